@@ -1,0 +1,79 @@
+"""CPU: pin the oracle against the golden vectors produced by the real reference and
+against the live cv2 build."""
+import numpy as np
+import pytest
+
+from oracle import compositor_np as C
+from oracle import farneback_np as FB
+from tests import golden_util as G
+
+Z = G.load("compositor_golden.npz")
+MASK_KEYS = ("mask_alpha", "mask_src", "mask_dst", "reset_mask")
+SPEC_KEYS = set(C.LayerSpec.__dataclass_fields__)
+
+
+def build_oracle_layers(z, name):
+    layers = []
+    for li, kw in enumerate(G.case_layers(z, name)):
+        spec = C.LayerSpec(**{k: v for k, v in kw.items() if k in SPEC_KEYS})
+        masks = {k: z[f"{name}/{k}{li}"] for k in MASK_KEYS if f"{name}/{k}{li}" in z.files}
+        srcs = G.case_sources(z, name, li)
+        h, w = z[f"{name}/flows"].shape[1:3]
+        layers.append(C.LayerOracle(spec, h, w, intro_masks=[m for _, m in srcs], **masks))
+    return layers
+
+
+@pytest.mark.parametrize("name", G.compositor_case_names(Z))
+def test_compositor_oracle_matches_reference(name):
+    flows = Z[f"{name}/flows"]
+    randoms = Z[f"{name}/randoms"]
+    layers = build_oracle_layers(Z, name)
+    comp = C.CompositorOracle(flows.shape[1], flows.shape[2], layers, (0x20, 0x40, 0x60))
+    ri = 0
+    for t in range(flows.shape[0]):
+        pm, rnd = {}, {}
+        for li, layer in enumerate(layers):
+            pm[li] = [G.pixmap_at(fr, t) for fr, _ in G.case_sources(Z, name, li)]
+            if layer.spec.reset_mode == "random":
+                rnd[li] = randoms[ri]
+                ri += 1
+        comp.update(flows[t], pm, rnd)
+        out = comp.render()
+        for li, layer in enumerate(layers):
+            if layer.data is not None:
+                np.testing.assert_array_equal(layer.data, Z[f"{name}/data{li}"][t], err_msg=f"{name} data t={t}")
+        np.testing.assert_array_equal(out, Z[f"{name}/render"][t], err_msg=f"{name} render t={t}")
+
+
+def test_reference_known_answers():
+    """tests/test_compositor.py:29-54 of the reference."""
+    k = G.load("kat_golden.npz")
+    flow = k["flow"]
+    lay = C.LayerOracle(C.LayerSpec(), 2, 3)
+    lay.update(flow)
+    assert tuple(lay.data[0, 0, :2]) == (1, 0) and tuple(lay.data[0, 1, :2]) == (1, 1)
+    np.testing.assert_array_equal(lay.data, k["moveref"])
+    lay = C.LayerOracle(C.LayerSpec(reset_mode="random", reset_random_factor=1), 2, 3)
+    np.random.seed(5)
+    lay.update(flow)
+    assert tuple(lay.data[0, 0, :2]) == (0, 0) and tuple(lay.data[0, 1, :2]) == (0, 1)
+    np.testing.assert_array_equal(lay.data, k["moveref_reset"])
+    rm = np.zeros((2, 3), np.float32)
+    rm[:, :1] = 1
+    lay = C.LayerOracle(C.LayerSpec(reset_mode="random", reset_random_factor=1), 2, 3, reset_mask=rm)
+    np.random.seed(5)
+    lay.update(flow)
+    assert tuple(lay.data[0, 0, :2]) == (0, 0) and tuple(lay.data[0, 1, :2]) == (1, 1)
+    np.testing.assert_array_equal(lay.data, k["moveref_reset_mask"])
+
+
+@pytest.mark.parametrize("params", [(0.5, 3, 15, 3, 5, 1.2), (0.5, 3, 19, 3, 7, 1.5), (0.7, 4, 15, 2, 5, 1.1)])
+def test_farneback_restatement_matches_cv2(params):
+    import cv2
+    from transflow_b200.synthetic import synthetic_clip
+    clip = synthetic_clip(120, 168, 2, seed=1)
+    g = [cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) for f in clip]
+    ref = cv2.calcOpticalFlowFarneback(g[0], g[1], None, *params, 0)
+    mine = FB.farneback(g[0], g[1], *params)
+    epe = np.linalg.norm(mine - ref, axis=-1)
+    assert epe.mean() < 1e-5 and epe.max() < 1e-4
