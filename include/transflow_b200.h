@@ -1,0 +1,201 @@
+/*
+ * transflow_b200 -- C ABI of the B200-native (sm_100a) transflow hot path.
+ *
+ * Dense optical flow per frame pair -> per-pixel flow accumulation -> pixmap remap.
+ * Every entry point is what a binding of the reference (ychalier/transflow, pure Python)
+ * would call in place of its cv2 / NumPy code; the reference interface each one replaces is
+ * cited as  transflow/<file>:<line>.
+ *
+ * Conventions
+ *   - every function returns 0 (TF_OK) or a negative tf_status; tf_last_error() gives text;
+ *   - all array arguments are DEVICE pointers to C-contiguous buffers owned by the caller
+ *     unless the name ends in _host; the library owns only per-handle scratch/state;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream;
+ *   - handles are not thread-safe: one handle <-> one stream at a time;
+ *   - there is no CPU fallback: a device that is not sm_100 yields TF_ERR_UNSUPPORTED_ARCH.
+ *
+ * Layouts (transflow/types.py:8-14, compositor/layers/data.py:8-12):
+ *   gray   uint8  (H, W)          bgr/rgb uint8 (H, W, 3)     rgba uint8 (H, W, 4)
+ *   flow   float32 (H, W, 2)      [...,0] = dx (columns), [...,1] = dy (rows)
+ *   data   int32  (H, W, 4) = (i, j, alpha, source)           (reference layers)
+ *          int32  (H, W, 8) = (r, g, b, alpha, source, i, j, frame)   (introduction layer)
+ */
+#ifndef TRANSFLOW_B200_H
+#define TRANSFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TF_API __attribute__((visibility("default")))
+#else
+#define TF_API
+#endif
+
+typedef enum {
+    TF_OK = 0,
+    TF_ERR_INVALID_ARG = -1,      /* -> ValueError   */
+    TF_ERR_CUDA = -2,             /* -> RuntimeError */
+    TF_ERR_UNSUPPORTED_ARCH = -3, /* -> RuntimeError */
+    TF_ERR_SHAPE = -4,            /* -> ValueError   */
+    TF_ERR_INDEX = -5             /* -> IndexError (gather index outside the frame) */
+} tf_status;
+
+TF_API int tf_version(void);
+TF_API const char* tf_last_error(void);
+/* 0 when `device` is an sm_100 part; fills sm count when sm_count != NULL. */
+TF_API int tf_device_check(int device, int* sm_count);
+/* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */
+TF_API uint64_t tf_launch_count(void);
+
+/* ---- frame prep: cv2.cvtColor(BGR2GRAY) at transflow/flow/sources/cv.py:465 ------------- */
+TF_API int tf_gray_from_bgr(const uint8_t* bgr, uint8_t* gray, int height, int width, void* stream);
+
+/* ---- Farneback: cv2.calcOpticalFlowFarneback at transflow/flow/sources/cv.py:477-490 ----- */
+typedef struct tf_farneback tf_farneback;
+/* Parameters = CvFlowConfig.fb_* (transflow/flow/sources/cv.py:275-281).  Only flags == 0 is
+ * supported (the reference default).  r_fp16 != 0 stores the polynomial-expansion tensors in
+ * half precision (compute stays fp32). */
+TF_API int tf_farneback_create(tf_farneback** out, int height, int width, double pyr_scale, int levels,
+                        int winsize, int iterations, int poly_n, double poly_sigma, int flags,
+                        int r_fp16);
+TF_API int tf_farneback_destroy(tf_farneback* h);
+/* Gaussian pyramid + polynomial expansion of one frame into slot 0 or 1 (cached across pairs,
+ * since a frame is the right image of one pair and the left image of the next). */
+TF_API int tf_farneback_prepare(tf_farneback* h, int slot, const uint8_t* gray, void* stream);
+/* Coarse-to-fine displacement solve between two prepared slots -> flow (H, W, 2).
+ * variant: 0 = fused streaming iteration kernel (default), 1 = unfused reference kernels.
+ * If clip != 0 the final clip of FlowSource.post_process (source.py:361-362) is fused into
+ * the last store. */
+TF_API int tf_farneback_solve(tf_farneback* h, int slot_left, int slot_right, float* flow, int variant,
+                       int clip, void* stream);
+/* prepare(0, left) + prepare(1, right) + solve(0, 1). */
+TF_API int tf_farneback_run(tf_farneback* h, const uint8_t* left, const uint8_t* right, float* flow,
+                     int variant, void* stream);
+TF_API int tf_farneback_num_levels(const tf_farneback* h);
+TF_API int tf_farneback_level_size(const tf_farneback* h, int level_index, int* width, int* height);
+/* Test hooks: copy stage outputs (as float32) to a device buffer.  what: 0 = pyramid image
+ * (h, w); 1 = polynomial expansion (5, h, w) of `slot`; 2 = flow (h, w, 2) at the end of the
+ * level during the last solve.  level_index 0 = coarsest. */
+TF_API int tf_farneback_debug_read(tf_farneback* h, int slot, int level_index, int what, float* out,
+                            void* stream);
+/* Algorithmic bytes moved per solved pair (SURVEY.md 8d model), for roofline reporting. */
+TF_API double tf_farneback_algorithmic_bytes(const tf_farneback* h, int reuse_r);
+
+/* ---- Horn-Schunck: transflow/flow/methods/horn_schunck.py:9-45 ---------------------------- */
+typedef struct tf_horn_schunck tf_horn_schunck;
+TF_API int tf_hs_create(tf_horn_schunck** out, int height, int width);
+TF_API int tf_hs_destroy(tf_horn_schunck* h);
+/* prev_flow may be NULL (first pair: u = v = 0).  delta < 0 disables the early exit
+ * (reference: delta is None).  sweeps_done_host (may be NULL) receives the sweeps executed. */
+TF_API int tf_hs_run(tf_horn_schunck* h, const uint8_t* left, const uint8_t* right,
+              const float* prev_flow, double alpha, int max_iters, double decay, double delta,
+              float* flow, int clip, int* sweeps_done_host, void* stream);
+
+/* ---- pyramidal Lucas-Kanade: transflow/flow/methods/lukas_kanade.py:9-36 ------------------ */
+typedef struct tf_lucas_kanade tf_lucas_kanade;
+TF_API int tf_lk_create(tf_lucas_kanade** out, int height, int width, int win_size, int max_level,
+                 int step);
+TF_API int tf_lk_destroy(tf_lucas_kanade* h);
+TF_API int tf_lk_run(tf_lucas_kanade* h, const uint8_t* left, const uint8_t* right, float* flow,
+              int clip, void* stream);
+
+/* ---- FlowSource.post_process: transflow/flow/sources/source.py:337-363 --------------------- */
+/* In place.  mask (float32 HxW) may be NULL.  forward != 0 runs the clip / round / scatter
+ * (last source in raster order wins) conversion of source.py:349-360; `owner` is an int32
+ * (H, W) scratch plane that must be all zero on entry and is left all zero on exit.
+ * The final clip (source.py:361-362) always runs. */
+TF_API int tf_flow_postprocess(float* flow, const float* mask, int forward, int32_t* owner, int height,
+                        int width, void* stream);
+
+/* ---- compositor: transflow/compositor/** ---------------------------------------------------- */
+enum { TF_LAYER_MOVEREF = 0, TF_LAYER_SUM = 1, TF_LAYER_STATIC = 2, TF_LAYER_INTRODUCTION = 3 };
+enum { TF_RESET_OFF = 0, TF_RESET_RANDOM = 1, TF_RESET_CONSTANT = 2, TF_RESET_LINEAR = 3 };
+
+/* Mirrors LayerConfig (transflow/config.py:57-104); booleans are 0/1 ints. */
+typedef struct {
+    int32_t kind;
+    int32_t transparent_pixels_can_move;
+    int32_t pixels_can_move_to_empty_spot;
+    int32_t pixels_can_move_to_filled_spot;
+    int32_t moving_pixels_leave_empty_spot;
+    int32_t reset_mode;
+    int32_t reset_source;
+    int32_t introduce_pixels_on_empty_spots;   /* no effect in the reference (quirk Q13) */
+    int32_t introduce_pixels_on_filled_spots;
+    int32_t introduce_moving_pixels;
+    int32_t introduce_unmoving_pixels;         /* no effect in the reference (quirk Q13) */
+    int32_t introduce_once;
+    int32_t introduce_on_all_filled_spots;
+    int32_t introduce_on_all_empty_spots;
+    float reset_constant_step;
+    float reset_random_factor; /* float32(reset_random_factor): threshold when reset_scale == NULL */
+    double reset_linear_factor;
+} tf_layer_config;
+
+typedef struct {
+    const uint8_t* pixels; /* device, (H, W, channels) */
+    int32_t channels;      /* 3 or 4 */
+    int32_t frame_number;  /* PixmapSourceInterface.frame_number (introduction layer) */
+} tf_pixmap;
+
+typedef struct tf_layer tf_layer;
+TF_API int tf_layer_create(tf_layer** out, int height, int width, const tf_layer_config* cfg);
+TF_API int tf_layer_destroy(tf_layer* l);
+/* Any pointer may be NULL = the reference default (all true / all 1).  mask_src, mask_dst:
+ * uint8 0/1 (H, W); mask_alpha: float32 (H, W); reset_scale: float32 (H, W) holding
+ * reset_random_factor*reset_mask (random), reset_constant_step*reset_mask (constant) or
+ * reset_mask (linear), evaluated by the host exactly as NumPy does. */
+TF_API int tf_layer_set_masks(tf_layer* l, const uint8_t* mask_src, const uint8_t* mask_dst,
+                       const float* mask_alpha, const float* reset_scale, void* stream);
+/* Layer.set_sources (compositor/layers/reference.py:54-56): introduction masks uint8 0/1
+ * (H, W) per source; re-applies the base source indices. */
+TF_API int tf_layer_set_sources(tf_layer* l, int n_sources, const uint8_t* const* intro_masks_host_array,
+                         void* stream);
+/* Layer.update(flow).  pixmaps: host array of n descriptors (device pixel pointers).
+ * random: float64 (H, W) draws of numpy.random.random (parity mode) or NULL -> counter-based
+ * Philox keyed by (rng_seed, frame counter, pixel).
+ * If rgb_inout != NULL the Layer.render + Compositor.render step for this layer is fused:
+ * first_layer != 0 starts from the constant background colour, otherwise from rgb_inout. */
+TF_API int tf_layer_update(tf_layer* l, const float* flow, const tf_pixmap* pixmaps_host, int n_pixmaps,
+                    const double* random, uint64_t rng_seed, uint8_t* rgb_inout, int first_layer,
+                    uint32_t background_rgb, void* stream);
+/* Layer.render (compositor/layers/layer.py:32-34): alpha *= mask_alpha in place; -> uint8 rgba. */
+TF_API int tf_layer_render(tf_layer* l, uint8_t* rgba_out, void* stream);
+/* Compositor.render (compositor/compositor.py:31-40) over n rendered layers (device rgba). */
+TF_API int tf_composite(const uint8_t* const* layer_rgba_host_array, int n_layers, uint32_t background_rgb,
+                 uint8_t* rgb_out, int height, int width, void* stream);
+/* Checkpoint interchange (pickled compositor, transflow/pipeline.py:225-242): state as the
+ * reference's NumPy arrays.  data: int32 (H, W, depth); rgba: uint8 (H, W, 4) (for the
+ * introduction layer rgba aliases data[..., :4] and may be NULL). */
+TF_API int tf_layer_depth(const tf_layer* l);
+TF_API int tf_layer_get_state(tf_layer* l, int32_t* data, uint8_t* rgba, void* stream);
+TF_API int tf_layer_set_state(tf_layer* l, const int32_t* data, const uint8_t* rgba, void* stream);
+/* Non-zero once a gather index left the frame (NumPy would have raised IndexError). */
+TF_API int tf_layer_poll_error(tf_layer* l, void* stream);
+/* Frames applied so far / introduced_once flag (for checkpoints). */
+TF_API int tf_layer_get_counters(const tf_layer* l, uint64_t* frames, int* introduced_once);
+TF_API int tf_layer_set_counters(tf_layer* l, uint64_t frames, int introduced_once);
+
+/* ---- multi-GPU flow hand-off over NVLink (frame pairs sharded across ranks) ---------------- */
+/* CUDA IPC plumbing so a producer rank's last flow kernel stores straight into the
+ * accumulator rank's ring slot (peer memory), followed by a release flag. */
+TF_API int tf_ipc_get_handle(const void* dev_ptr, uint8_t handle_out_host[64]);
+TF_API int tf_ipc_open_handle(const uint8_t handle_host[64], void** dev_ptr_out);
+TF_API int tf_ipc_close_handle(void* dev_ptr);
+/* Store `value` to a (possibly peer) 32-bit flag after all prior work on `stream`, with
+ * system-scope release semantics. */
+TF_API int tf_flag_signal(uint32_t* flag, uint32_t value, void* stream);
+/* Make `stream` wait until *flag >= value (driver stream memory op; no spinning kernel). */
+TF_API int tf_flag_wait_geq(uint32_t* flag, uint32_t value, void* stream);
+/* Peer copy of `bytes` with 128-bit stores issued by a kernel (dst may be peer memory). */
+TF_API int tf_copy_to_peer(void* dst, const void* src, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRANSFLOW_B200_H */

@@ -1,0 +1,146 @@
+"""Oracle for the flow side of the hot path.  TEST INFRASTRUCTURE (see ``oracle/__init__.py``).
+
+Farneback and pyramidal Lucas-Kanade are third-party arithmetic (``opencv-python``; this
+image: opencv-python-headless 4.13.0.92).  The oracle calls ``cv2`` with exactly the
+arguments of the reference's call sites; Horn-Schunck and the post-process step are
+reference-owned code and are restated in NumPy.
+"""
+import numpy as np
+
+
+def gray_from_bgr(bgr: np.ndarray) -> np.ndarray:
+    """``cv2.cvtColor(BGR2GRAY)`` as called at ``flow/sources/cv.py:465``: 15-bit fixed point
+    ``(3735 B + 19235 G + 9798 R + 16384) >> 15`` (bit-exact vs cv2 4.13)."""
+    b = bgr[..., 0].astype(np.int32)
+    g = bgr[..., 1].astype(np.int32)
+    r = bgr[..., 2].astype(np.int32)
+    return ((3735 * b + 19235 * g + 9798 * r + 16384) >> 15).astype(np.uint8)
+
+
+def farneback(left: np.ndarray, right: np.ndarray, pyr_scale=0.5, levels=3, winsize=15,
+              iterations=3, poly_n=5, poly_sigma=1.2, flags=0) -> np.ndarray:
+    """Call site ``flow/sources/cv.py:477-490`` (flags=0: the passed flow buffer is ignored)."""
+    import cv2
+    flow = np.zeros(left.shape + (2,), np.float32)
+    return cv2.calcOpticalFlowFarneback(prev=left, next=right, flow=flow, pyr_scale=pyr_scale,
+                                        levels=levels, winsize=winsize, iterations=iterations,
+                                        poly_n=poly_n, poly_sigma=poly_sigma,
+                                        flags=flags).astype(np.float32)
+
+
+def lucas_kanade(left: np.ndarray, right: np.ndarray, win_size=15, max_level=2, step=1) -> np.ndarray:
+    """``flow/methods/lukas_kanade.py:9-36``: PyrLK on the grid of every ``step``-th pixel,
+    status ignored, block-replicated back to (H, W)."""
+    import cv2
+    h, w = left.shape
+    gx, gy = np.meshgrid(np.arange(0, w, step), np.arange(0, h, step), indexing="xy")
+    p0 = np.stack([gx, gy], axis=-1).astype(np.float32)
+    rows, cols = p0.shape[:2]
+    p0 = p0.reshape(rows * cols, 1, 2)
+    p1 = p0.copy()
+    cv2.calcOpticalFlowPyrLK(left, right, p0, p1, winSize=(win_size, win_size), maxLevel=max_level)
+    flow = (p1 - p0).reshape(rows, cols, 2)
+    if step == 1:
+        return flow
+    return np.repeat(np.repeat(flow, step, axis=0), step, axis=1)[:h, :w].astype(np.float32)
+
+
+def _blur5(img_f32: np.ndarray) -> np.ndarray:
+    """``cv2.GaussianBlur(x, (5, 5), 0)``: separable [1 4 6 4 1]/16, BORDER_REFLECT_101."""
+    k = np.asarray([1, 4, 6, 4, 1], np.float32) / np.float32(16)
+    p = np.pad(img_f32, ((0, 0), (2, 2)), mode="reflect")
+    t = sum(k[j] * p[:, j:j + img_f32.shape[1]] for j in range(5))
+    p = np.pad(t, ((2, 2), (0, 0)), mode="reflect")
+    return sum(k[j] * p[j:j + img_f32.shape[0], :] for j in range(5)).astype(np.float32)
+
+
+def _fwd(x, axis):
+    """x shifted by +1 along axis with the last sample repeated (scipy 'reflect' == symmetric)."""
+    return np.concatenate([np.take(x, range(1, x.shape[axis]), axis=axis),
+                           np.take(x, [x.shape[axis] - 1], axis=axis)], axis=axis)
+
+
+def _avg3(u):
+    """``scipy.ndimage.convolve(u, [[1,2,1],[2,0,2],[1,2,1]]/12)`` with symmetric borders."""
+    p = np.pad(u, 1, mode="symmetric")
+    h, w = u.shape
+    s = (p[0:h, 0:w] + p[0:h, 2:w + 2] + p[2:h + 2, 0:w] + p[2:h + 2, 2:w + 2]
+         + 2 * (p[0:h, 1:w + 1] + p[2:h + 2, 1:w + 1] + p[1:h + 1, 0:w] + p[1:h + 1, 2:w + 2]))
+    return s / 12
+
+
+def horn_schunck(left, right, flow=None, alpha=1, max_iters=3, decay=0, delta=1,
+                 use_blur_from_cv2=True, sweeps_out=None):
+    """``flow/methods/horn_schunck.py:9-45``.
+
+    ``scipy.ndimage.convolve`` with a 2x2 kernel and mode='reflect' evaluates
+    out[i,j] = sum_{p,q in {0,1}} k[p,q] * x[i+1-p, j+1-q] with symmetric borders
+    (SURVEY.md A.3).  The early exit uses the matrix 2-norm (largest singular value) of
+    the change in ``u`` only.  ``sweeps_out`` (list) receives the number of sweeps executed.
+    """
+    if use_blur_from_cv2:
+        import cv2
+        a = cv2.GaussianBlur(left.astype(np.float32), (5, 5), 0)
+        b = cv2.GaussianBlur(right.astype(np.float32), (5, 5), 0)
+    else:
+        a, b = _blur5(left.astype(np.float32)), _blur5(right.astype(np.float32))
+    if flow is None:
+        u = np.zeros(a.shape)
+        v = np.zeros(a.shape)
+    else:
+        u = decay * flow[..., 0]
+        v = decay * flow[..., 1]
+
+    def d2x2(x, kx):
+        # kx[p][q] applies to x[i+1-p, j+1-q]
+        x01, x10, x11 = _fwd(x, 1), _fwd(x, 0), _fwd(_fwd(x, 0), 1)
+        return kx[0][0] * x11 + kx[0][1] * x10 + kx[1][0] * x01 + kx[1][1] * x
+    q = 0.25
+    xk = [[q, -q], [q, -q]]
+    yk = [[q, q], [-q, -q]]
+    tk = [[q, q], [q, q]]
+    ex = (d2x2(a, xk) + d2x2(b, xk)).astype(np.float32)
+    ey = (d2x2(a, yk) + d2x2(b, yk)).astype(np.float32)
+    et = (d2x2(b, tk) - d2x2(a, tk)).astype(np.float32)
+    n = 0
+    for _ in range(max_iters):
+        ua = _avg3(u).astype(u.dtype)
+        va = _avg3(v).astype(v.dtype)
+        c = (ex * ua + ey * va + et) / (alpha ** 2 + ex ** 2 + ey ** 2)
+        prev = u
+        u = ua - ex * c
+        v = va - ey * c
+        n += 1
+        if delta is not None and np.linalg.norm(u - prev, 2) < delta:
+            break
+    if sweeps_out is not None:
+        sweeps_out.append(n)
+    return np.stack([u, v], axis=-1).astype(np.float32)
+
+
+def post_process(flow: np.ndarray, forward: bool, mask=None) -> np.ndarray:
+    """``FlowSource.post_process`` (``flow/sources/source.py:337-363``) without filters/kernel.
+
+    forward: clip, half-even round, scatter source coordinates to their targets (last writer
+    in raster order wins), flow := origin - target; then the final clip (always).  Mutates
+    ``flow`` in place like the reference unless a mask forces a copy.
+    """
+    h, w = flow.shape[:2]
+    if mask is not None:
+        flow = np.multiply(np.asarray(mask, np.float32).reshape(h, w, 1), flow)
+    xs = np.arange(w, dtype=np.int32)[None, :]
+    ys = np.arange(h, dtype=np.int32)[:, None]
+    lo_x, hi_x, lo_y, hi_y = -xs, w - 1 - xs, -ys, h - 1 - ys
+    if forward:
+        np.clip(flow[..., 0], lo_x, hi_x, out=flow[..., 0])
+        np.clip(flow[..., 1], lo_y, hi_y, out=flow[..., 1])
+        fi = np.rint(flow).astype(np.int32)
+        off = (fi[..., 1] * w + fi[..., 0]).ravel()
+        src = np.nonzero(off)[0]
+        owner = np.arange(h * w)
+        owner[src + off[src]] = src          # duplicate targets: last (largest) source wins
+        flow[..., 0] = (owner % w).reshape(h, w) - xs
+        flow[..., 1] = (owner // w).reshape(h, w) - ys
+    np.clip(flow[..., 0], lo_x, hi_x, out=flow[..., 0])
+    np.clip(flow[..., 1], lo_y, hi_y, out=flow[..., 1])
+    return flow

@@ -1,0 +1,179 @@
+// Library globals, device checks, frame prep (BGR->gray) and flow post-processing kernels.
+#include "common.cuh"
+
+namespace tf {
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+static int g_arch_checked_device = -1;
+static int g_arch_status = TF_OK;
+static int g_sm_count = 148;
+
+int require_sm100() {
+    int dev = 0;
+    TF_CUDA(cudaGetDevice(&dev));
+    if (dev == g_arch_checked_device) {
+        if (g_arch_status != TF_OK)
+            return fail(g_arch_status, "device %d is not an sm_100 (B200) part; no fallback path exists", dev);
+        return TF_OK;
+    }
+    cudaDeviceProp prop;
+    TF_CUDA(cudaGetDeviceProperties(&prop, dev));
+    g_arch_checked_device = dev;
+    g_sm_count = prop.multiProcessorCount;
+    if (prop.major != 10) {
+        g_arch_status = TF_ERR_UNSUPPORTED_ARCH;
+        return fail(TF_ERR_UNSUPPORTED_ARCH,
+                    "device %d (%s, sm_%d%d) is not an sm_100 (B200) part; no fallback path exists",
+                    dev, prop.name, prop.major, prop.minor);
+    }
+    g_arch_status = TF_OK;
+    return TF_OK;
+}
+int sm_count() { return g_sm_count; }
+}  // namespace tf
+
+using namespace tf;
+
+extern "C" int tf_version(void) { return 100; }
+extern "C" const char* tf_last_error(void) { return tf::g_err; }
+extern "C" uint64_t tf_launch_count(void) { return tf::g_launches.load(); }
+
+extern "C" int tf_device_check(int device, int* sms) {
+    int count = 0;
+    TF_CUDA(cudaGetDeviceCount(&count));
+    TF_REQUIRE(device >= 0 && device < count, TF_ERR_INVALID_ARG, "no CUDA device %d (have %d)", device, count);
+    cudaDeviceProp prop;
+    TF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (sms) *sms = prop.multiProcessorCount;
+    TF_REQUIRE(prop.major == 10, TF_ERR_UNSUPPORTED_ARCH, "device %d (%s, sm_%d%d) is not sm_100", device,
+               prop.name, prop.major, prop.minor);
+    return TF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// BGR -> gray, bit-exact with cv2.cvtColor(BGR2GRAY) (flow/sources/cv.py:465):
+//   (3735*B + 19235*G + 9798*R + 16384) >> 15
+// 4 pixels per thread: three 32-bit loads (12 bytes) -> one 32-bit store.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gray1(uint32_t b, uint32_t g, uint32_t r) {
+    return (3735u * b + 19235u * g + 9798u * r + 16384u) >> 15;
+}
+
+__global__ void __launch_bounds__(256) k_gray_from_bgr(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray,
+                                                       size_t n) {
+    size_t quad = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t nq = n >> 2;
+    if (quad < nq) {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(bgr) + quad * 3;
+        uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+        uint32_t g0 = gray1(w0 & 255, (w0 >> 8) & 255, (w0 >> 16) & 255);
+        uint32_t g1 = gray1(w0 >> 24, w1 & 255, (w1 >> 8) & 255);
+        uint32_t g2 = gray1((w1 >> 16) & 255, w1 >> 24, w2 & 255);
+        uint32_t g3 = gray1((w2 >> 8) & 255, (w2 >> 16) & 255, w2 >> 24);
+        reinterpret_cast<uint32_t*>(gray)[quad] = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+    } else if (quad == nq) {
+        for (size_t i = nq * 4; i < n; i++) gray[i] = (uint8_t)gray1(bgr[3 * i], bgr[3 * i + 1], bgr[3 * i + 2]);
+    }
+}
+
+extern "C" int tf_gray_from_bgr(const uint8_t* bgr, uint8_t* gray, int height, int width, void* stream) {
+    TF_REQUIRE(bgr && gray, TF_ERR_INVALID_ARG, "tf_gray_from_bgr: null buffer");
+    TF_REQUIRE(height > 0 && width > 0, TF_ERR_SHAPE, "tf_gray_from_bgr: bad shape %dx%d", height, width);
+    TF_REQUIRE(((uintptr_t)bgr & 3) == 0 && ((uintptr_t)gray & 3) == 0, TF_ERR_INVALID_ARG,
+               "tf_gray_from_bgr: buffers must be 4-byte aligned");
+    if (int e = require_sm100()) return e;
+    size_t n = (size_t)height * width;
+    size_t threads = (n >> 2) + 1;
+    k_gray_from_bgr<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(bgr, gray, n);
+    TF_LAUNCHED();
+    return TF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// FlowSource.post_process (flow/sources/source.py:337-363)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 clip_flow(float2 f, int x, int y, int w, int h) {
+    // numpy.clip(flow, -x, W-1-x) with int32 bounds: float32 result
+    f.x = fminf(fmaxf(f.x, (float)(-x)), (float)(w - 1 - x));
+    f.y = fminf(fmaxf(f.y, (float)(-y)), (float)(h - 1 - y));
+    return f;
+}
+
+// backward direction: optional mask multiply + final clip.
+__global__ void __launch_bounds__(256) k_post_backward(float2* __restrict__ flow, const float* __restrict__ mask,
+                                                       int h, int w) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    size_t p = (size_t)y * w + x;
+    float2 f = flow[p];
+    if (mask) {
+        float m = mask[p];
+        f.x = __fmul_rn(m, f.x);
+        f.y = __fmul_rn(m, f.y);
+    }
+    flow[p] = clip_flow(f, x, y, w, h);
+}
+
+// forward pass 1: clip, round half-even, claim the target with atomicMax(source index + 1):
+// numpy.put with duplicate targets keeps the LAST source in raster order (quirk Q7).
+__global__ void __launch_bounds__(256) k_post_forward_scatter(const float2* __restrict__ flow,
+                                                              const float* __restrict__ mask,
+                                                              int* __restrict__ owner, int h, int w) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    int p = y * w + x;
+    float2 f = flow[p];
+    if (mask) {
+        float m = mask[p];
+        f.x = __fmul_rn(m, f.x);
+        f.y = __fmul_rn(m, f.y);
+    }
+    f = clip_flow(f, x, y, w, h);
+    int fx = __float2int_rn(f.x), fy = __float2int_rn(f.y);
+    int off = fy * w + fx;
+    if (off != 0) {
+        int q = min(max(p + off, 0), h * w - 1);  // numpy.put(mode="clip")
+        atomicMax(owner + q, p + 1);
+    }
+}
+
+// forward pass 2: flow := owner position - own position (0 where unclaimed); owner plane re-zeroed.
+__global__ void __launch_bounds__(256) k_post_forward_gather(float2* __restrict__ flow, int* __restrict__ owner,
+                                                             int h, int w) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    int p = y * w + x;
+    int o = owner[p];
+    float2 f = make_float2(0.f, 0.f);
+    if (o != 0) {
+        int s = o - 1;
+        owner[p] = 0;
+        f.x = (float)(s % w - x);
+        f.y = (float)(s / w - y);
+    }
+    flow[p] = f;  // already inside the frame: the final clip is the identity here
+}
+
+extern "C" int tf_flow_postprocess(float* flow, const float* mask, int forward, int32_t* owner, int height, int width,
+                                   void* stream) {
+    TF_REQUIRE(flow, TF_ERR_INVALID_ARG, "tf_flow_postprocess: null flow");
+    TF_REQUIRE(height > 0 && width > 0, TF_ERR_SHAPE, "tf_flow_postprocess: bad shape %dx%d", height, width);
+    TF_REQUIRE(!forward || owner, TF_ERR_INVALID_ARG, "tf_flow_postprocess: forward direction needs the owner plane");
+    if (int e = require_sm100()) return e;
+    dim3 grid(ceil_div(width, 256), height);
+    cudaStream_t st = as_stream(stream);
+    if (!forward) {
+        k_post_backward<<<grid, 256, 0, st>>>(reinterpret_cast<float2*>(flow), mask, height, width);
+        TF_LAUNCHED();
+    } else {
+        k_post_forward_scatter<<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(flow), mask, owner, height, width);
+        TF_LAUNCHED();
+        k_post_forward_gather<<<grid, 256, 0, st>>>(reinterpret_cast<float2*>(flow), owner, height, width);
+        TF_LAUNCHED();
+    }
+    return TF_OK;
+}

@@ -1,0 +1,618 @@
+// Farneback dense optical flow on device (replaces cv2.calcOpticalFlowFarneback as called at
+// transflow/flow/sources/cv.py:477-490, flags = 0).  Algorithm: OpenCV 4.x
+// modules/video/src/optflowgf.cpp (CPU path), restated in oracle/farneback_np.py.
+//
+// Stages per pyramid level (coarse -> fine):
+//   prepare : Gaussian blur of the FULL-RES frame + bilinear resize (separable, two passes)
+//             -> polynomial expansion R (5 coefficient planes, fp32 or fp16 storage)
+//   solve   : flow init (zeros / x(1/pyr_scale) bilinear upsample) -> iterations x
+//             [update-matrices -> (2m+1)^2 box sums -> 2x2 solve]
+//
+// Two solve variants share the same per-pixel math:
+//   variant 1 ("reference kernels"): M and the vertical sums are materialised in HBM;
+//   variant 0 ("fused streaming")  : one kernel per iteration, see fb_iter.cuh.
+#include "common.cuh"
+#include "fb_math.cuh"
+
+#include <math.h>
+#include <vector>
+
+using namespace tf;
+
+// ---------------------------------------------------------------------------------------------
+// host-side tables
+// ---------------------------------------------------------------------------------------------
+static int cv_round(double v) { return (int)nearbyint(v); }  // half-to-even, like cvRound
+
+static std::vector<float> gaussian_kernel(int ksz, double sigma) {
+    // cv::getGaussianKernel(ksz, sigma, CV_32F)
+    static const float k1[] = {1.f};
+    static const float k3[] = {0.25f, 0.5f, 0.25f};
+    static const float k5[] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
+    static const float k7[] = {0.03125f, 0.109375f, 0.21875f, 0.28125f, 0.21875f, 0.109375f, 0.03125f};
+    if (sigma <= 0 && ksz <= 7 && (ksz & 1)) {
+        const float* t = ksz == 1 ? k1 : ksz == 3 ? k3 : ksz == 5 ? k5 : k7;
+        return std::vector<float>(t, t + ksz);
+    }
+    double sig = sigma > 0 ? sigma : ((ksz - 1) * 0.5 - 1) * 0.3 + 0.8;
+    std::vector<double> g(ksz);
+    double sum = 0;
+    for (int i = 0; i < ksz; i++) {
+        double x = i - (ksz - 1) * 0.5;
+        g[i] = exp(-0.5 / (sig * sig) * x * x);
+        sum += g[i];
+    }
+    std::vector<float> out(ksz);
+    for (int i = 0; i < ksz; i++) out[i] = (float)(g[i] / sum);
+    return out;
+}
+
+// cv::resize INTER_LINEAR source index / weight for one axis
+static void linear_table(int dst, int src, std::vector<int>& s, std::vector<float>& t) {
+    s.resize(dst);
+    t.resize(dst);
+    double scale = (double)src / dst;
+    for (int d = 0; d < dst; d++) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int si = (int)floorf(f);
+        float ti = f - (float)si;
+        if (si < 0) { si = 0; ti = 0.f; }
+        if (si >= src - 1) { si = src - 1; ti = 0.f; }
+        s[d] = si;
+        t[d] = ti;
+    }
+}
+
+// FarnebackPrepareGaussian: taps and the four inverse-Gram terms
+static void prepare_poly(int n, double sigma, PolyCoef& pc) {
+    if (sigma < 1.1920929e-07) sigma = n * 0.3;
+    std::vector<float> g(2 * n + 1), xg(2 * n + 1), xxg(2 * n + 1);
+    double s = 0;
+    for (int x = -n; x <= n; x++) {
+        g[x + n] = (float)exp(-x * x / (2 * sigma * sigma));
+        s += g[x + n];
+    }
+    s = 1. / s;
+    for (int x = -n; x <= n; x++) {
+        g[x + n] = (float)(g[x + n] * s);
+        xg[x + n] = (float)(x * g[x + n]);
+        xxg[x + n] = (float)(x * x * g[x + n]);
+    }
+    double G[6][6] = {{0}};
+    for (int y = -n; y <= n; y++)
+        for (int x = -n; x <= n; x++) {
+            double gg = (double)g[y + n] * g[x + n];
+            G[0][0] += gg;
+            G[1][1] += gg * x * x;
+            G[3][3] += gg * x * x * x * x;
+            G[5][5] += gg * x * x * y * y;
+        }
+    G[2][2] = G[0][3] = G[0][4] = G[3][0] = G[4][0] = G[1][1];
+    G[4][4] = G[3][3];
+    G[3][4] = G[4][3] = G[5][5];
+    // invert the 6x6 by Gauss-Jordan with partial pivoting (double)
+    double A[6][12];
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 12; j++) A[i][j] = j < 6 ? G[i][j] : (j - 6 == i ? 1.0 : 0.0);
+    for (int c = 0; c < 6; c++) {
+        int piv = c;
+        for (int r = c + 1; r < 6; r++)
+            if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
+        for (int j = 0; j < 12; j++) std::swap(A[c][j], A[piv][j]);
+        double d = 1.0 / A[c][c];
+        for (int j = 0; j < 12; j++) A[c][j] *= d;
+        for (int r = 0; r < 6; r++)
+            if (r != c) {
+                double f = A[r][c];
+                for (int j = 0; j < 12; j++) A[r][j] -= f * A[c][j];
+            }
+    }
+    pc.n = n;
+    for (int k = 0; k <= n; k++) {
+        pc.g[k] = g[n + k];
+        pc.xg[k] = xg[n + k];
+        pc.xxg[k] = xxg[n + k];
+    }
+    pc.ig11 = (float)A[1][6 + 1];
+    pc.ig03 = (float)A[0][6 + 3];
+    pc.ig33 = (float)A[3][6 + 3];
+    pc.ig55 = (float)A[5][6 + 5];
+}
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct FbLevel {
+    int k, w, h, ksz;
+    double sigma;
+    float* gk;   // device Gaussian taps (ksz)
+    int* sx;     // device resize tables
+    float* tx;
+    int* sy;
+    float* ty;
+    float* img;     // pyramid image of the frame prepared last (h x w)
+    void* R[2];     // polynomial expansion per slot: 5 planes of h*w (float or __half)
+    float2* flow;   // per-level flow (the finest level writes into the caller's buffer)
+    float2* flow2;  // ping-pong partner for the fused iteration kernel
+    int* fsx;       // resize tables mapping the next-coarser level's flow onto this level
+    float* ftx;
+    int* fsy;
+    float* fty;
+};
+
+struct tf_farneback {
+    int H, W;
+    double pyr_scale;
+    int levels_req, winsize, iterations, poly_n, flags, r_fp16;
+    double poly_sigma;
+    PolyCoef pc;
+    std::vector<FbLevel> lv;  // coarse -> fine
+    float* T;                  // H x max(w) intermediate of the separable blur+resize
+    float* M;                  // variant 1: 5 planes at the finest level
+    double* VS;                // variant 1: vertical sums, 5 planes (double, like cv2's vsum)
+};
+
+// ---------------------------------------------------------------------------------------------
+// prepare kernels
+// ---------------------------------------------------------------------------------------------
+// Horizontal Gaussian (BORDER_REFLECT_101) evaluated only at the two source columns each output
+// column interpolates between, then the horizontal lerp: gray u8 (H, W) -> T f32 (H, w).
+__global__ void __launch_bounds__(256) k_fb_hpass(const uint8_t* __restrict__ gray, float* __restrict__ T,
+                                                  const float* __restrict__ gk, const int* __restrict__ sx,
+                                                  const float* __restrict__ tx, int H, int W, int w, int ksz) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = blockIdx.y;
+    if (x >= w) return;
+    const uint8_t* row = gray + (size_t)r * W;
+    int s0 = sx[x];
+    float t = tx[x];
+    int rad = ksz >> 1;
+    float a = 0.f, b = 0.f;
+    if (s0 - rad >= 0 && s0 + 1 + rad < W) {
+        for (int j = 0; j < ksz; j++) {
+            float g = gk[j];
+            a = fmaf(g, (float)row[s0 + j - rad], a);
+            b = fmaf(g, (float)row[s0 + 1 + j - rad], b);
+        }
+    } else {
+        int s1 = min(s0 + 1, W - 1);
+        for (int j = 0; j < ksz; j++) {
+            float g = gk[j];
+            a = fmaf(g, (float)row[reflect101(s0 + j - rad, W)], a);
+            b = fmaf(g, (float)row[reflect101(s1 + j - rad, W)], b);
+        }
+    }
+    T[(size_t)r * w + x] = a * (1.f - t) + b * t;
+}
+
+// Vertical Gaussian at the two source rows + vertical lerp: T (H, w) -> img (h, w).
+__global__ void __launch_bounds__(256) k_fb_vpass(const float* __restrict__ T, float* __restrict__ img,
+                                                  const float* __restrict__ gk, const int* __restrict__ sy,
+                                                  const float* __restrict__ ty, int H, int w, int h, int ksz) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    int s0 = sy[y];
+    int s1 = min(s0 + 1, H - 1);
+    float t = ty[y];
+    int rad = ksz >> 1;
+    float a = 0.f, b = 0.f;
+    for (int j = 0; j < ksz; j++) {
+        float g = gk[j];
+        a = fmaf(g, T[(size_t)reflect101(s0 + j - rad, H) * w + x], a);
+        b = fmaf(g, T[(size_t)reflect101(s1 + j - rad, H) * w + x], b);
+    }
+    img[(size_t)y * w + x] = a * (1.f - t) + b * t;
+}
+
+// Polynomial expansion (FarnebackPolyExp): separable (2n+1)^2 window, replicate borders.
+// Tile 64 x 16 outputs, 256 threads; every thread produces 4 consecutive outputs in each pass
+// from a register window, so shared-memory reads per output drop from (2n+1) to (2n+4)/4.
+// The tile's first pixel is subtracted before accumulation: the five stored coefficients are
+// invariant to a constant offset (the fit of a constant has zero derivative terms), and the
+// smaller magnitudes keep fp32 accumulation at the accuracy of cv2's double accumulators.
+template <int N, typename RT>
+__global__ void __launch_bounds__(256) k_fb_polyexp(const float* __restrict__ img, RT* __restrict__ R, int w, int h,
+                                                    PolyCoef pc) {
+    constexpr int TX = 64, TY = 16, SW = TX + 2 * N, SH = TY + 2 * N, SP = SW + 1;
+    __shared__ float sI[SH * SP];
+    __shared__ float sV[3][TY * SP];
+    int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    int tid = threadIdx.x;
+    float c0 = __ldg(img + (size_t)min(y0, h - 1) * w + min(x0, w - 1));
+    for (int i = tid; i < SH * SW; i += 256) {
+        int ly = i / SW, lx = i - ly * SW;
+        int gy = clampi(y0 + ly - N, 0, h - 1), gx = clampi(x0 + lx - N, 0, w - 1);
+        sI[ly * SP + lx] = __ldg(img + (size_t)gy * w + gx) - c0;
+    }
+    __syncthreads();
+    // vertical pass: SW columns x (TY / 4) row groups
+    for (int i = tid; i < SW * (TY / 4); i += 256) {
+        int lx = i % SW, gy = (i / SW) * 4;
+        float win[4 + 2 * N];
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * N; j++) win[j] = sI[(gy + j) * SP + lx];
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            float r0 = win[o + N] * pc.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; k++) {
+                float up = win[o + N - k], dn = win[o + N + k];
+                float p = up + dn;
+                r0 = fmaf(pc.g[k], p, r0);
+                r1 = fmaf(pc.xg[k], dn - up, r1);
+                r2 = fmaf(pc.xxg[k], p, r2);
+            }
+            sV[0][(gy + o) * SP + lx] = r0;
+            sV[1][(gy + o) * SP + lx] = r1;
+            sV[2][(gy + o) * SP + lx] = r2;
+        }
+    }
+    __syncthreads();
+    // horizontal pass: TY rows x (TX / 4) column groups = 256 work items
+    {
+        int ly = tid / (TX / 4), gx = (tid % (TX / 4)) * 4;
+        float w0[4 + 2 * N], w1[4 + 2 * N], w2[4 + 2 * N];
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * N; j++) {
+            w0[j] = sV[0][ly * SP + gx + j];
+            w1[j] = sV[1][ly * SP + gx + j];
+            w2[j] = sV[2][ly * SP + gx + j];
+        }
+        int y = y0 + ly;
+        size_t plane = (size_t)w * h;
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            float b1 = w0[o + N] * pc.g[0], b2 = 0.f, b3 = w1[o + N] * pc.g[0], b4 = 0.f, b5 = w2[o + N] * pc.g[0],
+                  b6 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; k++) {
+                float lo0 = w0[o + N - k], hi0 = w0[o + N + k];
+                float lo1 = w1[o + N - k], hi1 = w1[o + N + k];
+                float lo2 = w2[o + N - k], hi2 = w2[o + N + k];
+                float tg = hi0 + lo0;
+                b1 = fmaf(tg, pc.g[k], b1);
+                b4 = fmaf(tg, pc.xxg[k], b4);
+                b2 = fmaf(hi0 - lo0, pc.xg[k], b2);
+                b3 = fmaf(hi1 + lo1, pc.g[k], b3);
+                b6 = fmaf(hi1 - lo1, pc.xg[k], b6);
+                b5 = fmaf(hi2 + lo2, pc.g[k], b5);
+            }
+            int x = x0 + gx + o;
+            if (x < w && y < h) {
+                size_t at = (size_t)y * w + x;
+                store_r(R + at, b3 * pc.ig11);                                   // d/dy
+                store_r(R + plane + at, b2 * pc.ig11);                           // d/dx
+                store_r(R + 2 * plane + at, fmaf(b1, pc.ig03, b5 * pc.ig33));    // yy
+                store_r(R + 3 * plane + at, fmaf(b1, pc.ig03, b4 * pc.ig33));    // xx
+                store_r(R + 4 * plane + at, b6 * pc.ig55);                       // xy
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// solve kernels (variant 1: materialised M / vertical sums)
+// ---------------------------------------------------------------------------------------------
+// resize(prevFlow, INTER_LINEAR) * (1 / pyr_scale)
+__global__ void __launch_bounds__(256) k_fb_upsample_flow(const float2* __restrict__ src, float2* __restrict__ dst,
+                                                          const int* __restrict__ sx, const float* __restrict__ tx,
+                                                          const int* __restrict__ sy, const float* __restrict__ ty,
+                                                          int sw, int sh, int w, int h, float mul) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    int x0 = sx[x], y0 = sy[y];
+    int x1 = min(x0 + 1, sw - 1), y1 = min(y0 + 1, sh - 1);
+    float a = tx[x], b = ty[y];
+    float2 p00 = src[(size_t)y0 * sw + x0], p01 = src[(size_t)y0 * sw + x1];
+    float2 p10 = src[(size_t)y1 * sw + x0], p11 = src[(size_t)y1 * sw + x1];
+    float r0x = p00.x * (1.f - a) + p01.x * a, r0y = p00.y * (1.f - a) + p01.y * a;
+    float r1x = p10.x * (1.f - a) + p11.x * a, r1y = p10.y * (1.f - a) + p11.y * a;
+    dst[(size_t)y * w + x] = make_float2((r0x * (1.f - b) + r1x * b) * mul, (r0y * (1.f - b) + r1y * b) * mul);
+}
+
+template <typename RT>
+__global__ void __launch_bounds__(256) k_fb_update_matrices(const RT* __restrict__ R0, const RT* __restrict__ R1,
+                                                            const float2* __restrict__ flow, float* __restrict__ M,
+                                                            int w, int h) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    size_t plane = (size_t)w * h, at = (size_t)y * w + x;
+    float2 f = flow ? flow[at] : make_float2(0.f, 0.f);
+    float m[5];
+    fb_update_matrix<RT>(R0, R1, plane, w, h, x, y, f, m);
+#pragma unroll
+    for (int c = 0; c < 5; c++) M[c * plane + at] = m[c];
+}
+
+__global__ void __launch_bounds__(256) k_fb_box_v(const float* __restrict__ M, double* __restrict__ VS, int w, int h,
+                                                  int m) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    size_t plane = (size_t)w * h;
+    double acc[5] = {0., 0., 0., 0., 0.};
+    for (int k = -m; k <= m; k++) {
+        size_t at = (size_t)clampi(y + k, 0, h - 1) * w + x;
+#pragma unroll
+        for (int c = 0; c < 5; c++) acc[c] += (double)M[c * plane + at];
+    }
+#pragma unroll
+    for (int c = 0; c < 5; c++) VS[c * plane + (size_t)y * w + x] = acc[c];
+}
+
+__global__ void __launch_bounds__(256) k_fb_box_h_solve(const double* __restrict__ VS, float2* __restrict__ flow, int w,
+                                                        int h, int m, double scale, int clip) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    size_t plane = (size_t)w * h;
+    double acc[5] = {0., 0., 0., 0., 0.};
+    for (int k = -m; k <= m; k++) {
+        size_t at = (size_t)y * w + clampi(x + k, 0, w - 1);
+#pragma unroll
+        for (int c = 0; c < 5; c++) acc[c] += VS[c * plane + at];
+    }
+    float2 f = fb_solve(acc, scale);
+    if (clip) {
+        f.x = fminf(fmaxf(f.x, (float)(-x)), (float)(w - 1 - x));
+        f.y = fminf(fmaxf(f.y, (float)(-y)), (float)(h - 1 - y));
+    }
+    flow[(size_t)y * w + x] = f;
+}
+
+#include "fb_iter.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static int upload(T** dst, const std::vector<T>& v) {
+    TF_CUDA(cudaMalloc(reinterpret_cast<void**>(dst), v.size() * sizeof(T)));
+    TF_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return TF_OK;
+}
+
+extern "C" int tf_farneback_destroy(tf_farneback* h) {
+    if (!h) return TF_OK;
+    for (auto& l : h->lv) {
+        cudaFree(l.gk); cudaFree(l.sx); cudaFree(l.tx); cudaFree(l.sy); cudaFree(l.ty);
+        cudaFree(l.img); cudaFree(l.R[0]); cudaFree(l.R[1]); cudaFree(l.flow); cudaFree(l.flow2);
+        cudaFree(l.fsx); cudaFree(l.ftx); cudaFree(l.fsy); cudaFree(l.fty);
+    }
+    cudaFree(h->T); cudaFree(h->M); cudaFree(h->VS);
+    delete h;
+    return TF_OK;
+}
+
+extern "C" int tf_farneback_create(tf_farneback** out, int height, int width, double pyr_scale, int levels,
+                                   int winsize, int iterations, int poly_n, double poly_sigma, int flags, int r_fp16) {
+    TF_REQUIRE(out, TF_ERR_INVALID_ARG, "tf_farneback_create: null out");
+    TF_REQUIRE(height >= 2 && width >= 2 && (size_t)height * width < (1u << 30), TF_ERR_SHAPE,
+               "tf_farneback_create: bad shape %dx%d", height, width);
+    TF_REQUIRE(pyr_scale > 0 && pyr_scale < 1, TF_ERR_INVALID_ARG, "fb_pyr_scale must be in (0, 1), got %g", pyr_scale);
+    TF_REQUIRE(levels >= 0 && iterations >= 1, TF_ERR_INVALID_ARG, "fb_levels >= 0 and fb_iterations >= 1 required");
+    TF_REQUIRE(poly_n >= 1 && poly_n <= FB_MAX_POLY_N, TF_ERR_INVALID_ARG, "fb_poly_n must be in [1, %d], got %d",
+               FB_MAX_POLY_N, poly_n);
+    TF_REQUIRE(winsize >= 3 && winsize / 2 <= FB_MAX_WIN_RADIUS, TF_ERR_INVALID_ARG,
+               "fb_winsize must be in [3, %d], got %d (winsize < 3 hits an OpenCV running-sum quirk that is "
+               "outside the parity scope)", 2 * FB_MAX_WIN_RADIUS + 1, winsize);
+    TF_REQUIRE(flags == 0, TF_ERR_INVALID_ARG, "only fb_flags == 0 is supported (got %d)", flags);
+    if (int e = require_sm100()) return e;
+    tf_farneback* h = new (std::nothrow) tf_farneback();
+    TF_REQUIRE(h, TF_ERR_CUDA, "out of host memory");
+    h->H = height; h->W = width; h->pyr_scale = pyr_scale; h->levels_req = levels; h->winsize = winsize;
+    h->iterations = iterations; h->poly_n = poly_n; h->poly_sigma = poly_sigma; h->flags = flags;
+    h->r_fp16 = r_fp16 ? 1 : 0;
+    h->T = h->M = nullptr;
+    h->VS = nullptr;
+    prepare_poly(poly_n, poly_sigma, h->pc);
+    // level crop (min_size 32) exactly as optflowgf.cpp
+    int k = 0;
+    double scale = 1;
+    for (; k < levels; k++) {
+        scale *= pyr_scale;
+        if (width * scale < 32 || height * scale < 32) break;
+    }
+    int maxw = 0;
+    auto bail = [&](int e) { tf_farneback_destroy(h); return e; };
+    for (int lvl = k; lvl >= 0; lvl--) {
+        FbLevel L;
+        memset(&L, 0, sizeof(L));
+        scale = 1;
+        for (int i = 0; i < lvl; i++) scale *= pyr_scale;
+        L.k = lvl;
+        L.sigma = (1. / scale - 1) * 0.5;
+        L.ksz = std::max(cv_round(L.sigma * 5) | 1, 3);
+        L.w = cv_round(width * scale);
+        L.h = cv_round(height * scale);
+        if (L.w < 2 || L.h < 2) return bail(fail(TF_ERR_SHAPE, "pyramid level %d is %dx%d", lvl, L.w, L.h));
+        if (L.ksz / 2 >= std::min(width, height))
+            return bail(fail(TF_ERR_SHAPE, "frame too small for the level-%d Gaussian (%d taps)", lvl, L.ksz));
+        maxw = std::max(maxw, L.w);
+        std::vector<int> s;
+        std::vector<float> t;
+        if (int e = upload(&L.gk, gaussian_kernel(L.ksz, L.sigma))) return bail(e);
+        linear_table(L.w, width, s, t);
+        if (int e = upload(&L.sx, s)) return bail(e);
+        if (int e = upload(&L.tx, t)) return bail(e);
+        linear_table(L.h, height, s, t);
+        if (int e = upload(&L.sy, s)) return bail(e);
+        if (int e = upload(&L.ty, t)) return bail(e);
+        size_t n = (size_t)L.w * L.h;
+        size_t rbytes = n * 5 * (h->r_fp16 ? 2 : 4);
+        if (cudaMalloc(&L.img, n * 4) != cudaSuccess || cudaMalloc(&L.R[0], rbytes) != cudaSuccess ||
+            cudaMalloc(&L.R[1], rbytes) != cudaSuccess || cudaMalloc(&L.flow, n * 8) != cudaSuccess ||
+            cudaMalloc(&L.flow2, n * 8) != cudaSuccess)
+            return bail(fail(TF_ERR_CUDA, "cudaMalloc failed for pyramid level %d (%dx%d)", lvl, L.w, L.h));
+        if (!h->lv.empty()) {
+            const FbLevel& C = h->lv.back();  // next-coarser level
+            linear_table(L.w, C.w, s, t);
+            if (int e = upload(&L.fsx, s)) return bail(e);
+            if (int e = upload(&L.ftx, t)) return bail(e);
+            linear_table(L.h, C.h, s, t);
+            if (int e = upload(&L.fsy, s)) return bail(e);
+            if (int e = upload(&L.fty, t)) return bail(e);
+        }
+        h->lv.push_back(L);
+    }
+    if (cudaMalloc(&h->T, (size_t)height * maxw * 4) != cudaSuccess)
+        return bail(fail(TF_ERR_CUDA, "cudaMalloc failed for the blur intermediate"));
+    *out = h;
+    return TF_OK;
+}
+
+extern "C" int tf_farneback_num_levels(const tf_farneback* h) { return h ? (int)h->lv.size() : 0; }
+
+extern "C" int tf_farneback_level_size(const tf_farneback* h, int li, int* width, int* height) {
+    TF_REQUIRE(h && li >= 0 && li < (int)h->lv.size(), TF_ERR_INVALID_ARG, "tf_farneback_level_size: bad level %d", li);
+    if (width) *width = h->lv[li].w;
+    if (height) *height = h->lv[li].h;
+    return TF_OK;
+}
+
+template <typename RT>
+static int launch_polyexp(const tf_farneback* h, const FbLevel& L, int slot, cudaStream_t st) {
+    dim3 grid(ceil_div(L.w, 64), ceil_div(L.h, 16));
+    RT* R = reinterpret_cast<RT*>(L.R[slot]);
+    switch (h->poly_n) {
+#define TF_PE(N) case N: k_fb_polyexp<N, RT><<<grid, 256, 0, st>>>(L.img, R, L.w, L.h, h->pc); break;
+        TF_PE(1) TF_PE(2) TF_PE(3) TF_PE(4) TF_PE(5) TF_PE(6) TF_PE(7) TF_PE(8) TF_PE(9) TF_PE(10)
+#undef TF_PE
+        default: return fail(TF_ERR_INVALID_ARG, "unsupported poly_n %d", h->poly_n);
+    }
+    TF_LAUNCHED();
+    return TF_OK;
+}
+
+extern "C" int tf_farneback_prepare(tf_farneback* h, int slot, const uint8_t* gray, void* stream) {
+    TF_REQUIRE(h && gray, TF_ERR_INVALID_ARG, "tf_farneback_prepare: null argument");
+    TF_REQUIRE(slot == 0 || slot == 1, TF_ERR_INVALID_ARG, "tf_farneback_prepare: slot must be 0 or 1");
+    cudaStream_t st = as_stream(stream);
+    for (auto& L : h->lv) {
+        k_fb_hpass<<<dim3(ceil_div(L.w, 256), h->H), 256, 0, st>>>(gray, h->T, L.gk, L.sx, L.tx, h->H, h->W, L.w, L.ksz);
+        TF_LAUNCHED();
+        k_fb_vpass<<<dim3(ceil_div(L.w, 256), L.h), 256, 0, st>>>(h->T, L.img, L.gk, L.sy, L.ty, h->H, L.w, L.h, L.ksz);
+        TF_LAUNCHED();
+        int e = h->r_fp16 ? launch_polyexp<__half>(h, L, slot, st) : launch_polyexp<float>(h, L, slot, st);
+        if (e) return e;
+    }
+    return TF_OK;
+}
+
+template <typename RT>
+static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int variant, int clip, cudaStream_t st) {
+    int m = h->winsize / 2;
+    double scale = 1.0 / ((double)h->winsize * h->winsize);
+    if (variant == 1 && !h->M) {
+        size_t n = (size_t)h->lv.back().w * h->lv.back().h;
+        TF_CUDA(cudaMalloc(&h->M, n * 5 * sizeof(float)));
+        TF_CUDA(cudaMalloc(&h->VS, n * 5 * sizeof(double)));
+    }
+    const FbLevel* prev = nullptr;
+    for (size_t li = 0; li < h->lv.size(); li++) {
+        FbLevel& L = h->lv[li];
+        bool finest = li + 1 == h->lv.size();
+        float2* final_buf = finest ? flow_out : L.flow;
+        float2* other_buf = finest ? L.flow : L.flow2;
+        const RT* R0 = reinterpret_cast<const RT*>(L.R[sl]);
+        const RT* R1 = reinterpret_cast<const RT*>(L.R[sr]);
+        dim3 grid(ceil_div(L.w, 256), L.h);
+        bool zero_init = prev == nullptr;
+        // where the initial flow of this level goes: the buffer iteration 0 reads from
+        float2* init_buf = (variant == 1) ? final_buf : (((h->iterations - 1) & 1) ? final_buf : other_buf);
+        if (prev) {
+            k_fb_upsample_flow<<<grid, 256, 0, st>>>(prev->flow, init_buf, L.fsx, L.ftx, L.fsy, L.fty, prev->w, prev->h,
+                                                     L.w, L.h, (float)(1.0 / h->pyr_scale));
+            TF_LAUNCHED();
+        }
+        if (variant == 1) {
+            float2* flow = final_buf;
+            k_fb_update_matrices<RT><<<grid, 256, 0, st>>>(R0, R1, zero_init ? nullptr : flow, h->M, L.w, L.h);
+            TF_LAUNCHED();
+            for (int it = 0; it < h->iterations; it++) {
+                bool last = it + 1 == h->iterations;
+                k_fb_box_v<<<grid, 256, 0, st>>>(h->M, h->VS, L.w, L.h, m);
+                TF_LAUNCHED();
+                k_fb_box_h_solve<<<grid, 256, 0, st>>>(h->VS, flow, L.w, L.h, m, scale, clip && finest && last);
+                TF_LAUNCHED();
+                if (!last) {
+                    k_fb_update_matrices<RT><<<grid, 256, 0, st>>>(R0, R1, flow, h->M, L.w, L.h);
+                    TF_LAUNCHED();
+                }
+            }
+        } else {
+            if (int e = fb_iterate_fused<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest,
+                                             variant == 2, st))
+                return e;
+        }
+        prev = &L;
+    }
+    return TF_OK;
+}
+
+extern "C" int tf_farneback_solve(tf_farneback* h, int slot_left, int slot_right, float* flow, int variant, int clip,
+                                  void* stream) {
+    TF_REQUIRE(h && flow, TF_ERR_INVALID_ARG, "tf_farneback_solve: null argument");
+    TF_REQUIRE((slot_left == 0 || slot_left == 1) && (slot_right == 0 || slot_right == 1), TF_ERR_INVALID_ARG,
+               "tf_farneback_solve: slots must be 0 or 1");
+    TF_REQUIRE(variant >= 0 && variant <= 2, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
+    TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_solve: flow must be 8-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    float2* out = reinterpret_cast<float2*>(flow);
+    return h->r_fp16 ? solve_impl<__half>(h, slot_left, slot_right, out, variant, clip, st)
+                     : solve_impl<float>(h, slot_left, slot_right, out, variant, clip, st);
+}
+
+extern "C" int tf_farneback_run(tf_farneback* h, const uint8_t* left, const uint8_t* right, float* flow, int variant,
+                                void* stream) {
+    if (int e = tf_farneback_prepare(h, 0, left, stream)) return e;
+    if (int e = tf_farneback_prepare(h, 1, right, stream)) return e;
+    return tf_farneback_solve(h, 0, 1, flow, variant, 0, stream);
+}
+
+__global__ void __launch_bounds__(256) k_half_to_float(const __half* __restrict__ in, float* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __half2float(in[i]);
+}
+
+extern "C" int tf_farneback_debug_read(tf_farneback* h, int slot, int li, int what, float* out, void* stream) {
+    TF_REQUIRE(h && out, TF_ERR_INVALID_ARG, "tf_farneback_debug_read: null argument");
+    TF_REQUIRE(li >= 0 && li < (int)h->lv.size(), TF_ERR_INVALID_ARG, "tf_farneback_debug_read: bad level %d", li);
+    TF_REQUIRE(slot == 0 || slot == 1, TF_ERR_INVALID_ARG, "tf_farneback_debug_read: bad slot");
+    cudaStream_t st = as_stream(stream);
+    FbLevel& L = h->lv[li];
+    size_t n = (size_t)L.w * L.h;
+    if (what == 0) {
+        TF_CUDA(cudaMemcpyAsync(out, L.img, n * 4, cudaMemcpyDeviceToDevice, st));
+    } else if (what == 1) {
+        if (h->r_fp16) {
+            k_half_to_float<<<(unsigned)((n * 5 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __half*>(L.R[slot]),
+                                                                           out, n * 5);
+            TF_LAUNCHED();
+        } else {
+            TF_CUDA(cudaMemcpyAsync(out, L.R[slot], n * 20, cudaMemcpyDeviceToDevice, st));
+        }
+    } else if (what == 2) {
+        TF_REQUIRE(li + 1 < (int)h->lv.size(), TF_ERR_INVALID_ARG,
+                   "tf_farneback_debug_read: the finest level's flow is the solve output");
+        TF_CUDA(cudaMemcpyAsync(out, L.flow, n * 8, cudaMemcpyDeviceToDevice, st));
+    } else {
+        return fail(TF_ERR_INVALID_ARG, "tf_farneback_debug_read: unknown selector %d", what);
+    }
+    return TF_OK;
+}
+
+extern "C" double tf_farneback_algorithmic_bytes(const tf_farneback* h, int reuse_r) {
+    // (L+1)*N u8 reads + 20*S R writes (new frame) + T*S*(20+20+8+8);
+    // without reuse the second frame's pyramid + R are added.
+    if (!h) return 0;
+    double N = (double)h->H * h->W, S = 0;
+    for (auto& L : h->lv) S += (double)L.w * L.h;
+    double levels = (double)h->lv.size();
+    double b = levels * N + 20.0 * S + h->iterations * S * 56.0;
+    if (!reuse_r) b += levels * N + 20.0 * S;
+    return b;
+}

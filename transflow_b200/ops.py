@@ -1,0 +1,172 @@
+"""Thin, typed wrappers over the C ABI: torch CUDA tensors in, torch CUDA tensors out.
+
+Everything here runs on the current CUDA device and the current torch stream.  No function
+has a CPU path; CPU tensors raise.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+def _cuda(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (transflow_b200 has no CPU fallback)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def gray_from_bgr(bgr: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """``cv2.cvtColor(frame, COLOR_BGR2GRAY)`` (flow/sources/cv.py:465), bit-exact."""
+    bgr = _cuda(bgr, torch.uint8, "bgr")
+    if bgr.ndim != 3 or bgr.shape[2] != 3:
+        raise ValueError(f"bgr must be (H, W, 3), got {tuple(bgr.shape)}")
+    h, w = bgr.shape[:2]
+    if out is None:
+        out = torch.empty((h, w), dtype=torch.uint8, device=bgr.device)
+    check(_lib.load().tf_gray_from_bgr(ptr(bgr), ptr(out), h, w, stream_ptr()))
+    return out
+
+
+class Farneback:
+    """Device Farneback flow with the parameters of ``CvFlowConfig.fb_*`` (cv.py:275-281)."""
+
+    def __init__(self, height, width, pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5,
+                 poly_sigma=1.2, flags=0, r_fp16=False, variant=0):
+        self.lib = _lib.load()
+        self.h, self.w = int(height), int(width)
+        self.variant = int(variant)
+        self.handle = C.c_void_p()
+        check(self.lib.tf_farneback_create(C.byref(self.handle), self.h, self.w, float(pyr_scale), int(levels),
+                                           int(winsize), int(iterations), int(poly_n), float(poly_sigma),
+                                           int(flags), int(bool(r_fp16))))
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.tf_farneback_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    __del__ = close
+
+    def _gray(self, g, name):
+        g = _cuda(g, torch.uint8, name)
+        if tuple(g.shape) != (self.h, self.w):
+            raise ValueError(f"{name} must be ({self.h}, {self.w}), got {tuple(g.shape)}")
+        return g
+
+    def prepare(self, slot: int, gray: torch.Tensor):
+        check(self.lib.tf_farneback_prepare(self.handle, int(slot), ptr(self._gray(gray, "gray")), stream_ptr()))
+
+    def solve(self, slot_left: int, slot_right: int, out=None, clip=False) -> torch.Tensor:
+        if out is None:
+            out = torch.empty((self.h, self.w, 2), dtype=torch.float32, device="cuda")
+        check(self.lib.tf_farneback_solve(self.handle, int(slot_left), int(slot_right), ptr(out), self.variant,
+                                          int(bool(clip)), stream_ptr()))
+        return out
+
+    def __call__(self, left: torch.Tensor, right: torch.Tensor, out=None) -> torch.Tensor:
+        self.prepare(0, left)
+        self.prepare(1, right)
+        return self.solve(0, 1, out)
+
+    @property
+    def level_sizes(self):
+        n = self.lib.tf_farneback_num_levels(self.handle)
+        out = []
+        for i in range(n):
+            w, h = C.c_int(), C.c_int()
+            check(self.lib.tf_farneback_level_size(self.handle, i, C.byref(w), C.byref(h)))
+            out.append((h.value, w.value))
+        return out
+
+    def debug_read(self, slot: int, level_index: int, what: int) -> torch.Tensor:
+        h, w = self.level_sizes[level_index]
+        shape = {0: (h, w), 1: (5, h, w), 2: (h, w, 2)}[what]
+        out = torch.empty(shape, dtype=torch.float32, device="cuda")
+        check(self.lib.tf_farneback_debug_read(self.handle, slot, level_index, what, ptr(out), stream_ptr()))
+        return out
+
+    def algorithmic_bytes(self, reuse_r=True) -> float:
+        return float(self.lib.tf_farneback_algorithmic_bytes(self.handle, int(bool(reuse_r))))
+
+
+class HornSchunck:
+    """Device Horn-Schunck (flow/methods/horn_schunck.py:9-45)."""
+
+    def __init__(self, height, width):
+        self.lib = _lib.load()
+        self.h, self.w = int(height), int(width)
+        self.handle = C.c_void_p()
+        check(self.lib.tf_hs_create(C.byref(self.handle), self.h, self.w))
+        self.last_sweeps = 0
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.tf_hs_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    __del__ = close
+
+    def __call__(self, left, right, flow=None, alpha=1, max_iters=3, decay=0, delta=1, out=None, clip=False):
+        left = _cuda(left, torch.uint8, "left")
+        right = _cuda(right, torch.uint8, "right")
+        if tuple(left.shape) != (self.h, self.w) or tuple(right.shape) != (self.h, self.w):
+            raise ValueError(f"frames must be ({self.h}, {self.w})")
+        if flow is not None:
+            flow = _cuda(flow, torch.float32, "flow")
+        if out is None:
+            out = torch.empty((self.h, self.w, 2), dtype=torch.float32, device="cuda")
+        sweeps = C.c_int(0)
+        check(self.lib.tf_hs_run(self.handle, ptr(left), ptr(right), ptr(flow), float(alpha), int(max_iters),
+                                 float(decay), -1.0 if delta is None else float(delta), ptr(out),
+                                 int(bool(clip)), C.byref(sweeps), stream_ptr()))
+        self.last_sweeps = sweeps.value
+        return out
+
+
+class LucasKanade:
+    """Device pyramidal Lucas-Kanade on a dense grid (flow/methods/lukas_kanade.py:9-36)."""
+
+    def __init__(self, height, width, win_size=15, max_level=2, step=1):
+        self.lib = _lib.load()
+        self.h, self.w = int(height), int(width)
+        self.handle = C.c_void_p()
+        check(self.lib.tf_lk_create(C.byref(self.handle), self.h, self.w, int(win_size), int(max_level), int(step)))
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.tf_lk_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    __del__ = close
+
+    def __call__(self, left, right, out=None, clip=False):
+        left = _cuda(left, torch.uint8, "left")
+        right = _cuda(right, torch.uint8, "right")
+        if tuple(left.shape) != (self.h, self.w) or tuple(right.shape) != (self.h, self.w):
+            raise ValueError(f"frames must be ({self.h}, {self.w})")
+        if out is None:
+            out = torch.empty((self.h, self.w, 2), dtype=torch.float32, device="cuda")
+        check(self.lib.tf_lk_run(self.handle, ptr(left), ptr(right), ptr(out), int(bool(clip)), stream_ptr()))
+        return out
+
+
+class PostProcess:
+    """``FlowSource.post_process`` (flow/sources/source.py:337-363) in place on a device flow."""
+
+    def __init__(self, height, width, forward: bool, mask: torch.Tensor | None = None):
+        self.lib = _lib.load()
+        self.h, self.w, self.forward = int(height), int(width), bool(forward)
+        self.mask = None if mask is None else _cuda(mask, torch.float32, "mask").reshape(self.h, self.w)
+        self.owner = torch.zeros((self.h, self.w), dtype=torch.int32, device="cuda") if self.forward else None
+
+    def __call__(self, flow: torch.Tensor) -> torch.Tensor:
+        flow = _cuda(flow, torch.float32, "flow")
+        if tuple(flow.shape) != (self.h, self.w, 2):
+            raise ValueError(f"flow must be ({self.h}, {self.w}, 2), got {tuple(flow.shape)}")
+        check(self.lib.tf_flow_postprocess(ptr(flow), ptr(self.mask), int(self.forward), ptr(self.owner), self.h,
+                                           self.w, stream_ptr()))
+        return flow
