@@ -52,6 +52,14 @@ TF_API int tf_device_check(int device, int* sm_count);
 /* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */
 TF_API uint64_t tf_launch_count(void);
 
+/* Optional device timing of the dominant kernels (CUDA events on the launching stream), used by
+ * bench.py for the roofline figure.  Tags: 0 fused Farneback iteration (finest level), 1/2/3
+ * unfused update-matrices / vertical sums / horizontal sums+solve (finest level), 4 polynomial
+ * expansion (finest level), 5 compositor layer kernel, 6 forward post-process, 7 Horn-Schunck
+ * sweep, 8 Lucas-Kanade tracker (level 0).  tf_timer_read synchronises the device. */
+TF_API int tf_timer_enable(int on);
+TF_API int tf_timer_read(int tag, double* total_ms, uint64_t* launches);
+
 /* ---- frame prep: cv2.cvtColor(BGR2GRAY) at transflow/flow/sources/cv.py:465 ------------- */
 TF_API int tf_gray_from_bgr(const uint8_t* bgr, uint8_t* gray, int height, int width, void* stream);
 

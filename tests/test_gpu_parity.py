@@ -274,3 +274,103 @@ def test_horn_schunck_early_exit_decision():
         got = hs(dev(g0), dev(g1), None, alpha=1, max_iters=8, decay=0, delta=delta).cpu().numpy()
         assert hs.last_sweeps == sweeps[0], (delta, hs.last_sweeps, sweeps[0])
         assert epe(got, want)[1] <= 0.1
+
+
+@pytest.mark.parametrize("case", [(96, 128, 15, 2, 1), (120, 160, 15, 2, 4), (67, 93, 9, 3, 2), (270, 480, 15, 2, 1),
+                                  (40, 52, 21, 2, 1)])
+def test_lucas_kanade_matches_cv2(case):
+    from transflow_b200 import ops
+    h, w, win, lvl, step = case
+    g0, g1 = clip_pair(h, w, seed=7)
+    want = F.lucas_kanade(g0, g1, win, lvl, step)
+    got = ops.LucasKanade(h, w, win, lvl, step)(dev(g0), dev(g1)).cpu().numpy()
+    mean, mx = epe(got, want)
+    assert mean <= 0.01 and mx <= 0.1, (mean, mx)
+    # integer fixed-point inside: expect (near) bit-identical tracks
+    assert (np.abs(got - want).max(axis=-1) > 1e-3).mean() < 1e-3
+
+
+def test_lucas_kanade_golden_flow_source():
+    from transflow_b200 import ops
+    z = G.load("flow_golden.npz")
+    clip = z["clip"]
+    h, w = clip.shape[1:3]
+    grays = [ops.gray_from_bgr(dev(f)) for f in clip]
+    for name, step in (("lukas_kanade", 1), ("lukas_kanade_step4", 4)):
+        lk = ops.LucasKanade(h, w, 15, 2, step)
+        pp = ops.PostProcess(h, w, False)
+        for t in range(1, len(grays)):
+            got = pp(lk(grays[t], grays[t - 1])).cpu().numpy()     # backward: (cur, prev)
+            mean, mx = epe(got, z[f"{name}/backward"][t - 1])
+            assert mean <= 0.01 and mx <= 0.1, (name, t, mean, mx)
+
+
+# ------------------------------------------------------------------------------------------------
+# the plugin surface: CvFlowSource over an in-memory capture vs the reference's CvFlowSource output
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("direction", ["forward", "backward"])
+@pytest.mark.parametrize("name", ["farneback", "farneback_blurred", "horn_schunck", "horn_schunck_decay",
+                                  "lukas_kanade", "lukas_kanade_step4"])
+def test_flow_source_plugin_matches_reference(name, direction, tmp_path):
+    import json
+    from transflow_b200.flow import FlowSource
+    from transflow_b200.flow.sources.cv import ArrayCapture
+    z = G.load("flow_golden.npz")
+    clip = z["clip"]
+    cfg_path = tmp_path / "cfg.json"
+    cfg_path.write_text(str(z[f"{name}/config"]))
+    with FlowSource.from_args(ArrayCapture(clip, 25.0), cv_config=str(cfg_path), direction=direction) as src:
+        assert (src.width, src.height, src.framerate, src.length) == (clip.shape[2], clip.shape[1], 25.0, len(clip) - 1)
+        flows = list(src)
+    assert len(flows) == len(clip) - 1
+    want = z[f"{name}/{direction}"]
+    for t, got in enumerate(flows):
+        assert got.shape == want[t].shape and got.dtype == np.float32
+        if direction == "backward":
+            mean, mx = epe(got, want[t])
+            assert mean <= 0.01 and mx <= 0.1, (name, t, mean, mx)
+        else:
+            bad = (np.abs(got - want[t]).max(axis=-1) > 0).mean()
+            assert bad < 5e-3, (name, t, bad)
+
+
+def test_pipeline_end_to_end_matches_oracle(tmp_path):
+    """Whole in-process pipeline (flow source -> compositor -> host frames) on a small clip vs the
+    oracle chain fed with the device flows: frames bit-exact, checkpoint/resume diff == 0."""
+    import pickle
+    from transflow_b200.config import LayerConfig, PixmapSourceConfig
+    from transflow_b200.flow.sources.cv import ArrayCapture
+    from transflow_b200.pipeline import Config, Pipeline
+    from transflow_b200.pixmap.source import PixmapSource
+    from transflow_b200.synthetic import synthetic_clip
+    h, w, n = 96, 128, 6
+    clip = synthetic_clip(h, w, n, seed=9)
+    frames = {}
+    cfg = Config(ArrayCapture(clip), direction="backward", pixmap_sources=[PixmapSourceConfig("cnoise", layers=[0])],
+                 layers=[LayerConfig(0, "moveref")], output_path=lambda i, f: frames.__setitem__(i, f.copy()), seed=3,
+                 compositor_background="#102030")
+    pipe = Pipeline(cfg)
+    assert pipe.run() == n - 1 and sorted(frames) == list(range(n - 1))
+    # oracle replay with the same flows (recomputed through the plugin, device-resident)
+    from transflow_b200.flow import FlowSource
+    with FlowSource.from_args(ArrayCapture(clip), direction="backward") as src:
+        flows = list(src)
+    with PixmapSource.from_args("cnoise", (w, h), seed=3) as ps:
+        pix = next(ps)
+    ora = CN.LayerOracle(CN.LayerSpec(), h, w, intro_masks=[np.ones((h, w), bool)])
+    bg = np.empty((h, w, 3), np.uint8)
+    bg[:, :] = (0x10, 0x20, 0x30)
+    for t, flow in enumerate(flows):
+        ora.update(flow, [pix])
+        np.testing.assert_array_equal(frames[t], CN.composite(bg, [ora.render()]), err_msg=f"frame {t}")
+    # checkpoint interchange: pickled compositor restores to identical device state
+    blob = pickle.dumps(pipe.compositor)
+    clone = pickle.loads(blob)
+    np.testing.assert_array_equal(clone.layers[0].data, ora.data)
+    np.testing.assert_array_equal(clone.layers[0].rgba, ora.rgba)
+
+
+def test_no_cpu_fallback():
+    from transflow_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.gray_from_bgr(torch.zeros((4, 4, 3), dtype=torch.uint8))

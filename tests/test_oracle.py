@@ -132,3 +132,18 @@ def test_horn_schunck_own_blur_matches_cv2_blur():
     a = F.horn_schunck(g0, g1, use_blur_from_cv2=True)
     b = F.horn_schunck(g0, g1, use_blur_from_cv2=False)
     assert np.abs(a - b).max() < 1e-4
+
+
+@pytest.mark.parametrize("case", [(96, 128, 1, 3), (120, 160, 4, 1), (67, 93, 2, 5)])
+def test_lk_restatement_matches_cv2(case):
+    from oracle import flow_cv as F, lk_np
+    from transflow_b200.synthetic import synthetic_clip
+    import cv2
+    h, w, step, seed = case
+    clip = synthetic_clip(h, w, 2, seed=seed)
+    g0, g1 = F.gray_from_bgr(clip[0]), F.gray_from_bgr(clip[1])
+    np.testing.assert_array_equal(lk_np.pyr_down(g0), cv2.pyrDown(g0))
+    ref = F.lucas_kanade(g0, g1, 15, 2, step)
+    mine = lk_np.dense_flow(g0, g1, 15, 2, step)
+    d = np.abs(mine - ref).max(axis=-1)
+    assert (d > 0).mean() < 1e-3 and d.max() < 1e-3

@@ -61,6 +61,8 @@ SIGNATURES = {
     "tf_last_error": (C.c_char_p, []),
     "tf_device_check": (_i, [_i, _pi]),
     "tf_launch_count": (_u64, []),
+    "tf_timer_enable": (_i, [_i]),
+    "tf_timer_read": (_i, [_i, C.POINTER(_d), C.POINTER(_u64)]),
     "tf_gray_from_bgr": (_i, [_vp, _vp, _i, _i, _vp]),
     "tf_farneback_create": (_i, [C.POINTER(_vp), _i, _i, _d, _i, _i, _i, _i, _d, _i, _i]),
     "tf_farneback_destroy": (_i, [_vp]),
@@ -146,6 +148,22 @@ def ptr(t):
     if t is None:
         return C.c_void_p(0)
     return C.c_void_p(t.data_ptr())
+
+
+KERNEL_TAGS = {"fb_iter_finest": 0, "fb_um_finest": 1, "fb_boxv_finest": 2, "fb_boxh_finest": 3,
+               "fb_polyexp_finest": 4, "compositor_layer": 5, "post_forward": 6, "hs_sweep": 7,
+               "lk_track_finest": 8}
+
+
+def timer_enable(on: bool):
+    check(load().tf_timer_enable(int(bool(on))))
+
+
+def timer_read(tag: str):
+    """-> (total milliseconds, launches) of a tagged kernel since timer_enable(True)."""
+    ms, n = C.c_double(), C.c_uint64()
+    check(load().tf_timer_read(KERNEL_TAGS[tag], C.byref(ms), C.byref(n)))
+    return ms.value, n.value
 
 
 def launch_count() -> int:

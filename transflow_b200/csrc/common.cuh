@@ -46,6 +46,28 @@ inline int fail(int code, const char* fmt, ...) {
                             cudaGetErrorString(_e));                                           \
     } while (0)
 
+// ---- optional per-kernel device timing (bench.py roofline): CUDA events around tagged launches ----
+enum KernelTag {
+    TFK_FB_ITER_FINEST = 0,   // fused Farneback iteration kernel at the finest pyramid level
+    TFK_FB_UM_FINEST = 1,     // unfused variant: update-matrices
+    TFK_FB_BOXV_FINEST = 2,   //                  vertical box sums
+    TFK_FB_BOXH_FINEST = 3,   //                  horizontal box sums + solve
+    TFK_FB_POLYEXP_FINEST = 4,
+    TFK_COMPOSITOR_LAYER = 5, // fused move/reset/remap/composite kernel
+    TFK_POST_FORWARD = 6,
+    TFK_HS_SWEEP = 7,
+    TFK_LK_TRACK_FINEST = 8,
+    TFK_COUNT = 9
+};
+void timer_begin(int tag, cudaStream_t st);
+void timer_end(int tag, cudaStream_t st);
+struct ScopedKernelTimer {
+    int tag;
+    cudaStream_t st;
+    ScopedKernelTimer(int t, cudaStream_t s) : tag(t), st(s) { timer_begin(tag, st); }
+    ~ScopedKernelTimer() { timer_end(tag, st); }
+};
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -604,11 +604,17 @@ extern "C" int tf_layer_update(tf_layer* l, const float* flow, const tf_pixmap* 
                 k_mark_vacated<0><<<blocks1, 256, 0, st>>>(P, 1);
                 TF_LAUNCHED();
             }
-            k_reference_layer<TF_LAYER_MOVEREF><<<blocks4, 256, 0, st>>>(P);
+            {
+                ScopedKernelTimer timer(TFK_COMPOSITOR_LAYER, st);
+                k_reference_layer<TF_LAYER_MOVEREF><<<blocks4, 256, 0, st>>>(P);
+            }
             TF_LAUNCHED();
             l->cur ^= 1;
         } else if (kind == TF_LAYER_SUM) {
-            k_reference_layer<TF_LAYER_SUM><<<blocks4, 256, 0, st>>>(P);
+            {
+                ScopedKernelTimer timer(TFK_COMPOSITOR_LAYER, st);
+                k_reference_layer<TF_LAYER_SUM><<<blocks4, 256, 0, st>>>(P);
+            }
             TF_LAUNCHED();
         } else {
             P.do_introduce = !(l->cfg.introduce_once && l->introduced_once);

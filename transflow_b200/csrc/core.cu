@@ -33,7 +33,60 @@ int require_sm100() {
 int sm_count() { return g_sm_count; }
 }  // namespace tf
 
+// ---- kernel timers -------------------------------------------------------------------------------
+#include <vector>
+namespace tf {
+struct TimerSlot {
+    std::vector<cudaEvent_t> begin, end;
+    size_t used = 0;
+};
+static bool g_timing = false;
+static TimerSlot g_timers[TFK_COUNT];
+
+void timer_begin(int tag, cudaStream_t st) {
+    if (!g_timing || tag < 0) return;
+    TimerSlot& t = g_timers[tag];
+    if (t.used == t.begin.size()) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+        t.begin.push_back(a);
+        t.end.push_back(b);
+    }
+    cudaEventRecord(t.begin[t.used], st);
+}
+void timer_end(int tag, cudaStream_t st) {
+    if (!g_timing || tag < 0) return;
+    TimerSlot& t = g_timers[tag];
+    if (t.used < t.end.size()) {
+        cudaEventRecord(t.end[t.used], st);
+        t.used++;
+    }
+}
+}  // namespace tf
+
 using namespace tf;
+
+extern "C" int tf_timer_enable(int on) {
+    g_timing = on != 0;
+    if (on)
+        for (auto& t : g_timers) t.used = 0;
+    return TF_OK;
+}
+
+extern "C" int tf_timer_read(int tag, double* total_ms, uint64_t* launches) {
+    TF_REQUIRE(tag >= 0 && tag < TFK_COUNT, TF_ERR_INVALID_ARG, "tf_timer_read: bad tag %d", tag);
+    TF_CUDA(cudaDeviceSynchronize());
+    TimerSlot& t = g_timers[tag];
+    double sum = 0;
+    for (size_t i = 0; i < t.used; i++) {
+        float ms = 0.f;
+        TF_CUDA(cudaEventElapsedTime(&ms, t.begin[i], t.end[i]));
+        sum += ms;
+    }
+    if (total_ms) *total_ms = sum;
+    if (launches) *launches = t.used;
+    return TF_OK;
+}
 
 extern "C" int tf_version(void) { return 100; }
 extern "C" const char* tf_last_error(void) { return tf::g_err; }
@@ -170,6 +223,7 @@ extern "C" int tf_flow_postprocess(float* flow, const float* mask, int forward, 
         k_post_backward<<<grid, 256, 0, st>>>(reinterpret_cast<float2*>(flow), mask, height, width);
         TF_LAUNCHED();
     } else {
+        ScopedKernelTimer timer(TFK_POST_FORWARD, st);
         k_post_forward_scatter<<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(flow), mask, owner, height, width);
         TF_LAUNCHED();
         k_post_forward_gather<<<grid, 256, 0, st>>>(reinterpret_cast<float2*>(flow), owner, height, width);

@@ -477,9 +477,10 @@ template <typename RT>
 static int launch_polyexp(const tf_farneback* h, const FbLevel& L, int slot, cudaStream_t st) {
     dim3 grid(ceil_div(L.w, 64), ceil_div(L.h, 16));
     RT* R = reinterpret_cast<RT*>(L.R[slot]);
+    ScopedKernelTimer timer(&L == &h->lv.back() ? TFK_FB_POLYEXP_FINEST : -1, st);
     switch (h->poly_n) {
 #define TF_PE(N) case N: k_fb_polyexp<N, RT><<<grid, 256, 0, st>>>(L.img, R, L.w, L.h, h->pc); break;
-        TF_PE(1) TF_PE(2) TF_PE(3) TF_PE(4) TF_PE(5) TF_PE(6) TF_PE(7) TF_PE(8) TF_PE(9) TF_PE(10)
+            TF_PE(1) TF_PE(2) TF_PE(3) TF_PE(4) TF_PE(5) TF_PE(6) TF_PE(7) TF_PE(8) TF_PE(9) TF_PE(10)
 #undef TF_PE
         default: return fail(TF_ERR_INVALID_ARG, "unsupported poly_n %d", h->poly_n);
     }
@@ -530,22 +531,32 @@ static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int var
         }
         if (variant == 1) {
             float2* flow = final_buf;
-            k_fb_update_matrices<RT><<<grid, 256, 0, st>>>(R0, R1, zero_init ? nullptr : flow, h->M, L.w, L.h);
+            {
+                ScopedKernelTimer timer(finest ? TFK_FB_UM_FINEST : -1, st);
+                k_fb_update_matrices<RT><<<grid, 256, 0, st>>>(R0, R1, zero_init ? nullptr : flow, h->M, L.w, L.h);
+            }
             TF_LAUNCHED();
             for (int it = 0; it < h->iterations; it++) {
                 bool last = it + 1 == h->iterations;
-                k_fb_box_v<<<grid, 256, 0, st>>>(h->M, h->VS, L.w, L.h, m);
+                {
+                    ScopedKernelTimer timer(finest ? TFK_FB_BOXV_FINEST : -1, st);
+                    k_fb_box_v<<<grid, 256, 0, st>>>(h->M, h->VS, L.w, L.h, m);
+                }
                 TF_LAUNCHED();
-                k_fb_box_h_solve<<<grid, 256, 0, st>>>(h->VS, flow, L.w, L.h, m, scale, clip && finest && last);
+                {
+                    ScopedKernelTimer timer(finest ? TFK_FB_BOXH_FINEST : -1, st);
+                    k_fb_box_h_solve<<<grid, 256, 0, st>>>(h->VS, flow, L.w, L.h, m, scale, clip && finest && last);
+                }
                 TF_LAUNCHED();
                 if (!last) {
+                    ScopedKernelTimer timer(finest ? TFK_FB_UM_FINEST : -1, st);
                     k_fb_update_matrices<RT><<<grid, 256, 0, st>>>(R0, R1, flow, h->M, L.w, L.h);
-                    TF_LAUNCHED();
                 }
+                if (!last) TF_LAUNCHED();
             }
         } else {
             if (int e = fb_iterate_fused<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest,
-                                             variant == 2, st))
+                                             variant == 2, finest, st))
                 return e;
         }
         prev = &L;

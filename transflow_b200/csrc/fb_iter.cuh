@@ -126,7 +126,7 @@ static size_t fb_iter_smem_bytes(int m) {
 // last iteration lands in `final_buf`.  init_in_final tells where the initial flow currently is.
 template <typename RT>
 static int fb_iterate_fused(tf_farneback* h, FbLevel& L, const RT* R0, const RT* R1, float2* final_buf,
-                            float2* other_buf, bool zero_init, int clip, int precise, cudaStream_t st) {
+                            float2* other_buf, bool zero_init, int clip, int precise, bool finest, cudaStream_t st) {
     int m = h->winsize / 2;
     double scale = 1.0 / ((double)h->winsize * h->winsize);
     int strips = ceil_div(L.w, FBI_TX);
@@ -149,7 +149,10 @@ static int fb_iterate_fused(tf_farneback* h, FbLevel& L, const RT* R0, const RT*
         float2* dst = ((T - 1 - it) & 1) ? other_buf : final_buf;
         float2* src = ((T - 1 - it) & 1) ? final_buf : other_buf;
         const float2* in = (it == 0 && zero_init) ? nullptr : src;
-        kern<<<grid, FBI_NT, smem, st>>>(R0, R1, in, dst, L.w, L.h, m, scale, rows, clip && it + 1 == T);
+        {
+            ScopedKernelTimer timer(finest ? TFK_FB_ITER_FINEST : -1, st);
+            kern<<<grid, FBI_NT, smem, st>>>(R0, R1, in, dst, L.w, L.h, m, scale, rows, clip && it + 1 == T);
+        }
         TF_LAUNCHED();
     }
     return TF_OK;

@@ -309,8 +309,11 @@ extern "C" int tf_hs_run(tf_horn_schunck* h, const uint8_t* left, const uint8_t*
             TF_CUDA(cudaMemsetAsync(h->colsq, 0, W * 4, st));
             TF_CUDA(cudaMemsetAsync(h->stats, 0, 16, st));
         }
-        k_hs_sweep<<<grid, block, 0, st>>>(h->Ex, h->Ey, h->Et, h->uv[cur], h->uv[cur ^ 1], (float)(alpha * alpha), H, W,
-                                           0, track ? h->rowsq : nullptr, h->colsq, h->stats);
+        {
+            ScopedKernelTimer timer(TFK_HS_SWEEP, st);
+            k_hs_sweep<<<grid, block, 0, st>>>(h->Ex, h->Ey, h->Et, h->uv[cur], h->uv[cur ^ 1], (float)(alpha * alpha), H,
+                                               W, 0, track ? h->rowsq : nullptr, h->colsq, h->stats);
+        }
         TF_LAUNCHED();
         cur ^= 1;
         done++;

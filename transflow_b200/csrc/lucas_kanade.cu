@@ -1,7 +1,302 @@
-// placeholder replaced below in this round: pyramidal Lucas-Kanade
+// Pyramidal Lucas-Kanade on a dense grid of every `step`-th pixel, replacing
+// cv2.calcOpticalFlowPyrLK as called at transflow/flow/methods/lukas_kanade.py:26-32
+// (winSize (w, w), maxLevel, criteria COUNT+EPS 30 / 0.01, flags 0, minEigThreshold 1e-4;
+// status is never read by the reference).  Algorithm: OpenCV 4.x lkpyramid.cpp, restated in
+// oracle/lk_np.py: integer pyrDown, int16 Scharr derivatives, 14-bit bilinear weights, 5
+// fractional bits on intensities, float32 2x2 solve.
+//
+// This path is bounded by integer ALU throughput, not HBM: one thread tracks one
+// point; window rows slide through registers so every tap is loaded once per pass.
 #include "common.cuh"
+
+#include <vector>
+
 using namespace tf;
-struct tf_lucas_kanade { int H, W; };
-extern "C" int tf_lk_create(tf_lucas_kanade** out, int, int, int, int, int) { (void)out; return fail(TF_ERR_INVALID_ARG, "lucas-kanade: not built yet"); }
-extern "C" int tf_lk_destroy(tf_lucas_kanade*) { return TF_OK; }
-extern "C" int tf_lk_run(tf_lucas_kanade*, const uint8_t*, const uint8_t*, float*, int, void*) { return fail(TF_ERR_INVALID_ARG, "lucas-kanade: not built yet"); }
+
+#define LK_W_BITS 14
+
+struct LkLevel {
+    int w, h;
+    uint8_t* img[2];  // [0] = left/prev, [1] = right/next; level 0 aliases the caller's frames
+    short2* deriv;    // Scharr (Ix, Iy) of the left image
+};
+
+struct tf_lucas_kanade {
+    int H, W, win, max_level, step;
+    int gw, gh;  // grid of tracked points
+    std::vector<LkLevel> lv;
+    float2* next_pts;
+};
+
+// cv::pyrDown (uint8): [1 4 6 4 1] x [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8
+__global__ void __launch_bounds__(256) k_lk_pyrdown(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int sw,
+                                                    int sh, int dw, int dh) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dw) return;
+    const int k[5] = {1, 4, 6, 4, 1};
+    int cx[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) cx[j] = reflect101(2 * x + j - 2, sw);
+    int acc = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        const uint8_t* row = src + (size_t)reflect101(2 * y + i - 2, sh) * sw;
+        int r = 0;
+#pragma unroll
+        for (int j = 0; j < 5; j++) r += k[j] * (int)row[cx[j]];
+        acc += k[i] * r;
+    }
+    dst[(size_t)y * dw + x] = (uint8_t)((acc + 128) >> 8);
+}
+
+// ScharrDerivInvoker: Ix = t0(x+1) - t0(x-1), t0 = 3*(I(y-1) + I(y+1)) + 10*I(y);
+//                     Iy = 3*(t1(x-1) + t1(x+1)) + 10*t1(x), t1 = I(y+1) - I(y-1)
+__global__ void __launch_bounds__(256) k_lk_scharr(const uint8_t* __restrict__ img, short2* __restrict__ deriv, int w,
+                                                   int h) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    int xl = reflect101(x - 1, w), xr = reflect101(x + 1, w);
+    const uint8_t* ru = img + (size_t)reflect101(y - 1, h) * w;
+    const uint8_t* rc = img + (size_t)y * w;
+    const uint8_t* rd = img + (size_t)reflect101(y + 1, h) * w;
+    int t0l = ((int)ru[xl] + (int)rd[xl]) * 3 + (int)rc[xl] * 10;
+    int t0r = ((int)ru[xr] + (int)rd[xr]) * 3 + (int)rc[xr] * 10;
+    int t1l = (int)rd[xl] - (int)ru[xl], t1c = (int)rd[x] - (int)ru[x], t1r = (int)rd[xr] - (int)ru[xr];
+    deriv[(size_t)y * w + x] = make_short2((short)(t0r - t0l), (short)((t1r + t1l) * 3 + t1c * 10));
+}
+
+struct LkWeights {
+    int w00, w01, w10, w11;
+};
+
+__device__ __forceinline__ LkWeights lk_weights(float a, float b) {
+    LkWeights q;
+    const float s = (float)(1 << LK_W_BITS);
+    q.w00 = __float2int_rn((1.f - a) * (1.f - b) * s);
+    q.w01 = __float2int_rn(a * (1.f - b) * s);
+    q.w10 = __float2int_rn((1.f - a) * b * s);
+    q.w11 = (1 << LK_W_BITS) - q.w00 - q.w01 - q.w10;
+    return q;
+}
+
+__device__ __forceinline__ int lk_descale(int v, int n) { return (v + (1 << (n - 1))) >> n; }
+
+// image tap with the REFLECT_101 border cv2 pads the pyramid with; derivative tap with zeros
+__device__ __forceinline__ int lk_img(const uint8_t* __restrict__ img, int x, int y, int w, int h, bool inside) {
+    if (!inside) {
+        x = reflect101(x, w);
+        y = reflect101(y, h);
+    }
+    return (int)__ldg(img + (size_t)y * w + x);
+}
+__device__ __forceinline__ short2 lk_der(const short2* __restrict__ d, int x, int y, int w, int h, bool inside) {
+    if (!inside && ((unsigned)x >= (unsigned)w || (unsigned)y >= (unsigned)h)) return make_short2(0, 0);
+    return __ldg(d + (size_t)y * w + x);
+}
+
+// Interpolated template values of the window pixel (x, y) given the four taps.
+struct LkTemplate {
+    int ival, ix, iy;
+};
+
+// One pyramid level of LKTrackerInvoker for every grid point.
+__global__ void __launch_bounds__(128) k_lk_track(const uint8_t* __restrict__ I, const uint8_t* __restrict__ J,
+                                                  const short2* __restrict__ D, float2* __restrict__ next_pts, int w,
+                                                  int h, int gw, int gh, int step, int win, int level, int is_top) {
+    int gx = blockIdx.x * 32 + (threadIdx.x & 31), gy = blockIdx.y * 4 + (threadIdx.x >> 5);
+    if (gx >= gw || gy >= gh) return;
+    size_t pid = (size_t)gy * gw + gx;
+    const float lscale = 1.f / (float)(1 << level);
+    const float half = (float)(win - 1) * 0.5f;
+    float px = (float)(gx * step) * lscale, py = (float)(gy * step) * lscale;
+    float2 np;
+    if (is_top) {
+        np = make_float2(px, py);
+    } else {
+        np = next_pts[pid];
+        np.x *= 2.f;
+        np.y *= 2.f;
+    }
+    next_pts[pid] = np;  // stored before any test (points that fail keep this value)
+    px -= half;
+    py -= half;
+    int ipx = (int)floorf(px), ipy = (int)floorf(py);
+    if (ipx < -win || ipx >= w || ipy < -win || ipy >= h) return;
+    LkWeights q = lk_weights(px - (float)ipx, py - (float)ipy);
+    const bool insideI = ipx >= 0 && ipy >= 0 && ipx + win < w && ipy + win < h;
+    const float FLT_SCALE = 1.f / (float)(1 << 20);
+
+    // pass 1: covariance of the interpolated derivatives
+    float A11 = 0.f, A12 = 0.f, A22 = 0.f;
+    for (int y = 0; y < win; y++) {
+        short2 d0 = lk_der(D, ipx, ipy + y, w, h, insideI), d1 = lk_der(D, ipx, ipy + y + 1, w, h, insideI);
+        for (int x = 0; x < win; x++) {
+            short2 e0 = lk_der(D, ipx + x + 1, ipy + y, w, h, insideI), e1 = lk_der(D, ipx + x + 1, ipy + y + 1, w, h, insideI);
+            int ixv = lk_descale(d0.x * q.w00 + e0.x * q.w01 + d1.x * q.w10 + e1.x * q.w11, LK_W_BITS);
+            int iyv = lk_descale(d0.y * q.w00 + e0.y * q.w01 + d1.y * q.w10 + e1.y * q.w11, LK_W_BITS);
+            A11 += (float)(ixv * ixv);
+            A12 += (float)(ixv * iyv);
+            A22 += (float)(iyv * iyv);
+            d0 = e0;
+            d1 = e1;
+        }
+    }
+    A11 *= FLT_SCALE;
+    A12 *= FLT_SCALE;
+    A22 *= FLT_SCALE;
+    float Dd = A11 * A22 - A12 * A12;
+    float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+    if (minEig < 1e-4f || Dd < 1.1920929e-07f) return;
+    Dd = 1.f / Dd;
+
+    float nx = np.x - half, ny = np.y - half;
+    float pdx = 0.f, pdy = 0.f;
+    for (int j = 0; j < 30; j++) {
+        int inx = (int)floorf(nx), iny = (int)floorf(ny);
+        if (inx < -win || inx >= w || iny < -win || iny >= h) break;
+        LkWeights r = lk_weights(nx - (float)inx, ny - (float)iny);
+        const bool insideJ = inx >= 0 && iny >= 0 && inx + win < w && iny + win < h;
+        float b1 = 0.f, b2 = 0.f;
+        for (int y = 0; y < win; y++) {
+            short2 d0 = lk_der(D, ipx, ipy + y, w, h, insideI), d1 = lk_der(D, ipx, ipy + y + 1, w, h, insideI);
+            int i0 = lk_img(I, ipx, ipy + y, w, h, insideI), i1 = lk_img(I, ipx, ipy + y + 1, w, h, insideI);
+            int j0 = lk_img(J, inx, iny + y, w, h, insideJ), j1 = lk_img(J, inx, iny + y + 1, w, h, insideJ);
+            for (int x = 0; x < win; x++) {
+                short2 e0 = lk_der(D, ipx + x + 1, ipy + y, w, h, insideI),
+                       e1 = lk_der(D, ipx + x + 1, ipy + y + 1, w, h, insideI);
+                int k0 = lk_img(I, ipx + x + 1, ipy + y, w, h, insideI), k1 = lk_img(I, ipx + x + 1, ipy + y + 1, w, h, insideI);
+                int l0 = lk_img(J, inx + x + 1, iny + y, w, h, insideJ), l1 = lk_img(J, inx + x + 1, iny + y + 1, w, h, insideJ);
+                int ival = lk_descale(i0 * q.w00 + k0 * q.w01 + i1 * q.w10 + k1 * q.w11, LK_W_BITS - 5);
+                int ixv = lk_descale(d0.x * q.w00 + e0.x * q.w01 + d1.x * q.w10 + e1.x * q.w11, LK_W_BITS);
+                int iyv = lk_descale(d0.y * q.w00 + e0.y * q.w01 + d1.y * q.w10 + e1.y * q.w11, LK_W_BITS);
+                int diff = lk_descale(j0 * r.w00 + l0 * r.w01 + j1 * r.w10 + l1 * r.w11, LK_W_BITS - 5) - ival;
+                b1 += (float)(diff * ixv);
+                b2 += (float)(diff * iyv);
+                d0 = e0; d1 = e1; i0 = k0; i1 = k1; j0 = l0; j1 = l1;
+            }
+        }
+        b1 *= FLT_SCALE;
+        b2 *= FLT_SCALE;
+        float dx = (A12 * b2 - A22 * b1) * Dd, dy = (A12 * b1 - A11 * b2) * Dd;
+        nx += dx;
+        ny += dy;
+        float2 o = make_float2(nx + half, ny + half);
+        if ((double)dx * dx + (double)dy * dy <= 1e-4) {  // epsilon^2, epsilon = 0.01
+            next_pts[pid] = o;
+            break;
+        }
+        if (j > 0 && fabsf(dx + pdx) < 0.01f && fabsf(dy + pdy) < 0.01f) {
+            o.x -= dx * 0.5f;
+            o.y -= dy * 0.5f;
+            next_pts[pid] = o;
+            break;
+        }
+        next_pts[pid] = o;
+        pdx = dx;
+        pdy = dy;
+    }
+}
+
+// flow = p1 - p0, block-replicated (numpy.kron) back to (H, W), optional final clip
+__global__ void __launch_bounds__(256) k_lk_flow_out(const float2* __restrict__ next_pts, float2* __restrict__ flow,
+                                                     int H, int W, int gw, int step, int clip) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    int gx = x / step, gy = y / step;
+    float2 n = __ldg(next_pts + (size_t)gy * gw + gx);
+    float2 f = make_float2(n.x - (float)(gx * step), n.y - (float)(gy * step));
+    if (clip) {
+        f.x = fminf(fmaxf(f.x, (float)(-x)), (float)(W - 1 - x));
+        f.y = fminf(fmaxf(f.y, (float)(-y)), (float)(H - 1 - y));
+    }
+    flow[(size_t)y * W + x] = f;
+}
+
+extern "C" int tf_lk_destroy(tf_lucas_kanade* h) {
+    if (!h) return TF_OK;
+    for (size_t i = 0; i < h->lv.size(); i++) {
+        if (i > 0) {
+            cudaFree(h->lv[i].img[0]);
+            cudaFree(h->lv[i].img[1]);
+        }
+        cudaFree(h->lv[i].deriv);
+    }
+    cudaFree(h->next_pts);
+    delete h;
+    return TF_OK;
+}
+
+extern "C" int tf_lk_create(tf_lucas_kanade** out, int height, int width, int win_size, int max_level, int step) {
+    TF_REQUIRE(out, TF_ERR_INVALID_ARG, "tf_lk_create: null out");
+    TF_REQUIRE(height >= 2 && width >= 2 && (size_t)height * width < (1u << 30), TF_ERR_SHAPE,
+               "tf_lk_create: bad shape %dx%d", height, width);
+    TF_REQUIRE(win_size >= 3 && win_size <= 63, TF_ERR_INVALID_ARG, "lk_window_size must be in [3, 63], got %d", win_size);
+    TF_REQUIRE(max_level >= 0 && max_level <= 10, TF_ERR_INVALID_ARG, "lk_max_level must be in [0, 10], got %d", max_level);
+    TF_REQUIRE(step >= 1, TF_ERR_INVALID_ARG, "lk_step must be >= 1, got %d", step);
+    if (int e = require_sm100()) return e;
+    tf_lucas_kanade* h = new (std::nothrow) tf_lucas_kanade();
+    TF_REQUIRE(h, TF_ERR_CUDA, "out of host memory");
+    h->H = height; h->W = width; h->win = win_size; h->max_level = max_level; h->step = step;
+    h->gw = ceil_div(width, step);
+    h->gh = ceil_div(height, step);
+    h->next_pts = nullptr;
+    auto bail = [&](int e) { tf_lk_destroy(h); return e; };
+    int w = width, hh = height;
+    for (int l = 0; l <= max_level; l++) {
+        LkLevel L;
+        memset(&L, 0, sizeof(L));
+        L.w = w;
+        L.h = hh;
+        size_t n = (size_t)w * hh;
+        if (l > 0 && (cudaMalloc(&L.img[0], n) != cudaSuccess || cudaMalloc(&L.img[1], n) != cudaSuccess))
+            return bail(fail(TF_ERR_CUDA, "tf_lk_create: allocation failed"));
+        if (cudaMalloc(&L.deriv, n * sizeof(short2)) != cudaSuccess) return bail(fail(TF_ERR_CUDA, "tf_lk_create: allocation failed"));
+        h->lv.push_back(L);
+        // buildOpticalFlowPyramid stops when the NEXT level would not exceed the window
+        w = (w + 1) / 2;
+        hh = (hh + 1) / 2;
+        if (w <= win_size || hh <= win_size) break;
+    }
+    if (cudaMalloc(&h->next_pts, (size_t)h->gw * h->gh * sizeof(float2)) != cudaSuccess)
+        return bail(fail(TF_ERR_CUDA, "tf_lk_create: allocation failed"));
+    *out = h;
+    return TF_OK;
+}
+
+extern "C" int tf_lk_run(tf_lucas_kanade* h, const uint8_t* left, const uint8_t* right, float* flow, int clip,
+                         void* stream) {
+    TF_REQUIRE(h && left && right && flow, TF_ERR_INVALID_ARG, "tf_lk_run: null argument");
+    TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_lk_run: flow must be 8-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    h->lv[0].img[0] = const_cast<uint8_t*>(left);
+    h->lv[0].img[1] = const_cast<uint8_t*>(right);
+    for (size_t l = 0; l < h->lv.size(); l++) {
+        LkLevel& L = h->lv[l];
+        if (l > 0) {
+            LkLevel& P = h->lv[l - 1];
+            dim3 grid(ceil_div(L.w, 256), L.h);
+            for (int s = 0; s < 2; s++) {
+                k_lk_pyrdown<<<grid, 256, 0, st>>>(P.img[s], L.img[s], P.w, P.h, L.w, L.h);
+                TF_LAUNCHED();
+            }
+        }
+        k_lk_scharr<<<dim3(ceil_div(L.w, 256), L.h), 256, 0, st>>>(L.img[0], L.deriv, L.w, L.h);
+        TF_LAUNCHED();
+    }
+    int top = (int)h->lv.size() - 1;
+    dim3 tgrid(ceil_div(h->gw, 32), ceil_div(h->gh, 4));
+    for (int l = top; l >= 0; l--) {
+        LkLevel& L = h->lv[l];
+        {
+            ScopedKernelTimer timer(l == 0 ? TFK_LK_TRACK_FINEST : -1, st);
+            k_lk_track<<<tgrid, 128, 0, st>>>(L.img[0], L.img[1], L.deriv, h->next_pts, L.w, L.h, h->gw, h->gh, h->step,
+                                              h->win, l, l == top);
+        }
+        TF_LAUNCHED();
+    }
+    k_lk_flow_out<<<dim3(ceil_div(h->W, 256), h->H), 256, 0, st>>>(h->next_pts, reinterpret_cast<float2*>(flow), h->H, h->W,
+                                                                   h->gw, h->step, clip);
+    TF_LAUNCHED();
+    h->lv[0].img[0] = h->lv[0].img[1] = nullptr;
+    return TF_OK;
+}

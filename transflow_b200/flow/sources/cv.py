@@ -1,0 +1,316 @@
+"""``CvFlowSource`` on device (drop-in for ``transflow/flow/sources/cv.py:271-524``).
+
+Same ``CvFlowConfig`` fields (``method, fb_*, hs_*, lk_*``) and JSON files, same
+``Builder`` / ``rewind`` / ``next`` contract.  Frames still arrive from ``cv2.VideoCapture``
+(host decode is out of scope) or from an in-memory ``ArrayCapture``; every
+arithmetic step after the decode -- BGR->gray, Farneback / Horn-Schunck / Lucas-Kanade, the
+post-process -- runs in CUDA.  A frame's Farneback pyramid + polynomial expansion is computed
+once and reused as the other side of the next pair.
+"""
+import enum
+import json
+import re
+
+import numpy as np
+import torch
+
+from .source import FlowSource
+from ... import ops
+
+
+class CvFlowConfig:
+
+    _DEFAULTS = dict(fb_pyr_scale=0.5, fb_levels=3, fb_winsize=15, fb_iterations=3, fb_poly_n=5,
+                     fb_poly_sigma=1.2, fb_flags=0, hs_alpha=1, hs_iterations=3, hs_decay=0, hs_delta=1,
+                     lk_window_size=15, lk_max_level=2, lk_step=1)
+
+    def __init__(self, method="farneback", show_window=False, **params):
+        unknown = set(params) - set(self._DEFAULTS)
+        if unknown:
+            raise TypeError(f"Unexpected CvFlowConfig fields: {sorted(unknown)}")
+        self.method = CvFlowSource.Method.from_string(method) if isinstance(method, str) else method
+        for name, default in self._DEFAULTS.items():
+            setattr(self, name, params.get(name, default))
+        self.show_window = show_window  # the Qt tuning window is out of scope (PySide6 UI)
+        self.window = None
+
+    def start(self):
+        if self.show_window:
+            raise NotImplementedError("the Qt configuration window is not part of the accelerated path")
+
+    def update(self, attrname, value):
+        if attrname == "method" and isinstance(value, str):
+            value = CvFlowSource.Method.from_string(value)
+        setattr(self, attrname, value)
+
+    def reset(self):
+        self.method = CvFlowSource.Method.FARNEBACK
+        for name, default in self._DEFAULTS.items():
+            setattr(self, name, default)
+        self.hs_decay = 0.95  # the reference's reset() differs from its constructor here (cv.py:321)
+
+    def to_dict(self):
+        d = {"method": CvFlowSource.Method.to_string(self.method)}
+        d.update({name: getattr(self, name) for name in self._DEFAULTS})
+        return d
+
+    def to_file(self, path: str):
+        with open(path, "w", encoding="utf8") as file:
+            json.dump(self.to_dict(), file, indent=4)
+
+    @classmethod
+    def from_file(cls, path: str):
+        with open(path, "r", encoding="utf8") as file:
+            return cls(**json.load(file))
+
+
+class ArrayCapture:
+    """In-memory stand-in for ``cv2.VideoCapture`` over a ``(T, H, W, 3) uint8`` BGR array
+    (NumPy, or a CUDA tensor to skip the per-frame upload)."""
+
+    def __init__(self, frames, fps: float = 25.0):
+        self.frames = frames
+        self.fps = float(fps)
+        self.pos = 0
+
+    def read(self):
+        if self.pos >= len(self.frames):
+            return False, None
+        frame = self.frames[self.pos]
+        self.pos += 1
+        return True, frame
+
+    def get(self, prop):
+        import cv2
+        if prop == cv2.CAP_PROP_FRAME_WIDTH:
+            return self.frames.shape[2]
+        if prop == cv2.CAP_PROP_FRAME_HEIGHT:
+            return self.frames.shape[1]
+        if prop == cv2.CAP_PROP_FPS:
+            return self.fps
+        if prop == cv2.CAP_PROP_FRAME_COUNT:
+            return len(self.frames)
+        return 0
+
+    def set(self, prop, value):
+        import cv2
+        if prop == cv2.CAP_PROP_POS_MSEC:
+            self.pos = int(round(value / 1000.0 * self.fps))
+        return True
+
+    def release(self):
+        pass
+
+
+class CvFlowSource(FlowSource):
+
+    @enum.unique
+    class Method(enum.Enum):
+        FARNEBACK = 0
+        HORN_SCHUNCK = 1
+        LUKAS_KANADE = 2
+        LITEFLOWNET = 3
+
+        @classmethod
+        def from_string(cls, string: str):
+            for m, s in _METHOD_NAMES.items():
+                if s == string:
+                    return cls[m]
+            raise ValueError(f"Invalid Flow Method: {string}")
+
+        @staticmethod
+        def to_string(method):
+            if method.name in _METHOD_NAMES:
+                return _METHOD_NAMES[method.name]
+            raise ValueError(f"Unknown flow method {method}")
+
+    class Builder(FlowSource.Builder):
+
+        def __init__(self, file, config: CvFlowConfig, size=None, **kwargs):
+            super().__init__(**kwargs)
+            self.file = file
+            self.config = config
+            self.size = size
+            self.capture = None
+
+        @property
+        def cls(self):
+            return CvFlowSource
+
+        def build(self):
+            import cv2
+            if hasattr(self.file, "read") and hasattr(self.file, "get"):
+                self.capture = self.file          # an already-open capture (e.g. ArrayCapture)
+            elif re.match(r"\d+", self.file):
+                self.capture = cv2.VideoCapture(int(self.file))  # webcam index
+            else:
+                self.capture = cv2.VideoCapture(self.file)
+            if self.size is not None:
+                self.capture.set(cv2.CAP_PROP_FRAME_WIDTH, self.size[0])
+                self.capture.set(cv2.CAP_PROP_FRAME_HEIGHT, self.size[1])
+            self.width = int(self.capture.get(cv2.CAP_PROP_FRAME_WIDTH))
+            self.height = int(self.capture.get(cv2.CAP_PROP_FRAME_HEIGHT))
+            self.framerate = float(self.capture.get(cv2.CAP_PROP_FPS))
+            self.base_length = int(self.capture.get(cv2.CAP_PROP_FRAME_COUNT)) - 1
+            super().build()
+
+        def args(self):
+            return [self.capture, self.config, *FlowSource.Builder.args(self)]
+
+    def __init__(self, capture, config: CvFlowConfig, *args, **kwargs):
+        self.config = config
+        self.capture = capture
+        self.prev_gray = None
+        self._slot = 0          # Farneback slot holding prev_gray's pyramid + expansion
+        self._engine = None
+        self._engine_key = None
+        self._stage = None      # pinned host staging for uploads
+        self._copy_stream = None
+        self._lookahead = None
+        #: read one frame ahead so its H2D copy overlaps the current frame's kernels
+        self.prefetch = True
+        self.config.start()
+        FlowSource.__init__(self, *args, **kwargs)
+
+    def validate(self):
+        super().validate()
+        self.assert_type("config", CvFlowConfig)
+        if not (hasattr(self.capture, "read") and hasattr(self.capture, "release")):
+            raise ValueError("Attribute capture has incorrect type")
+
+    # -- frame prep (cv.py:461-466): resize NEAREST on the host if needed, upload, gray on device ------
+    def _upload(self, frame) -> torch.Tensor:
+        """Start the H2D copy of a decoded BGR frame on the side stream; returns the device frame.
+        CUDA tensors pass through, pinned CPU tensors are copied directly, NumPy frames go through
+        a pinned staging buffer."""
+        if isinstance(frame, torch.Tensor) and frame.is_cuda:
+            return frame
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        if isinstance(frame, torch.Tensor) and frame.is_pinned():
+            src = frame
+        else:
+            if isinstance(frame, torch.Tensor):
+                frame = frame.numpy()
+            if frame.shape[1] != self.width or frame.shape[0] != self.height:
+                import cv2
+                frame = cv2.resize(frame, dsize=(self.width, self.height), interpolation=cv2.INTER_NEAREST)
+            if self._stage is None:
+                self._stage = [torch.empty((self.height, self.width, 3), dtype=torch.uint8).pin_memory()
+                               for _ in range(2)]
+                self._stage_events = [None, None]
+            k = self._stage_index = (getattr(self, "_stage_index", 0) + 1) & 1
+            if self._stage_events[k] is not None:
+                self._stage_events[k].synchronize()     # the previous copy out of this buffer is done
+            self._stage[k].numpy()[...] = frame
+            src = self._stage[k]
+        with torch.cuda.stream(self._copy_stream):
+            dev = src.cuda(non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        if src is not frame and self._stage is not None:
+            self._stage_events[self._stage_index] = ev
+        dev._tf_ready = ev
+        return dev
+
+    def _gray_on_device(self, frame) -> torch.Tensor:
+        bgr = self._upload(frame)
+        ev = getattr(bgr, "_tf_ready", None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            bgr.record_stream(torch.cuda.current_stream())
+        return ops.gray_from_bgr(bgr)
+
+    def _read_frame(self):
+        """capture.read() with a one-frame look-ahead: the next frame's upload overlaps this
+        frame's kernels."""
+        if self._lookahead is not None:
+            item = self._lookahead
+            self._lookahead = None
+        else:
+            ok, frame = self.capture.read()
+            item = (ok, self._upload(frame) if (ok and frame is not None) else None)
+        if self.prefetch and item[0] and item[1] is not None:
+            ok, frame = self.capture.read()
+            self._lookahead = (ok, self._upload(frame) if (ok and frame is not None) else None)
+        return item
+
+    def _method_engine(self):
+        c = self.config
+        m = c.method
+        if m == CvFlowSource.Method.FARNEBACK:
+            key = ("fb", c.fb_pyr_scale, c.fb_levels, c.fb_winsize, c.fb_iterations, c.fb_poly_n, c.fb_poly_sigma,
+                   c.fb_flags)
+            make = lambda: ops.Farneback(self.height, self.width, c.fb_pyr_scale, c.fb_levels, c.fb_winsize,  # noqa: E731
+                                         c.fb_iterations, c.fb_poly_n, c.fb_poly_sigma, c.fb_flags)
+        elif m == CvFlowSource.Method.HORN_SCHUNCK:
+            key = ("hs",)
+            make = lambda: ops.HornSchunck(self.height, self.width)  # noqa: E731
+        elif m == CvFlowSource.Method.LUKAS_KANADE:
+            key = ("lk", c.lk_window_size, c.lk_max_level, c.lk_step)
+            make = lambda: ops.LucasKanade(self.height, self.width, c.lk_window_size, c.lk_max_level, c.lk_step)  # noqa: E731
+        elif m == CvFlowSource.Method.LITEFLOWNET:
+            raise ImportError("LiteFlowNet method cannot be used: it is outside the accelerated path (SURVEY.md #9)")
+        else:
+            raise ValueError(f"Unknown flow method '{m}'")
+        if key != self._engine_key:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = make()
+            self._engine_key = key
+            self._prepared = False
+        return self._engine
+
+    def rewind(self):
+        import cv2
+        FlowSource.rewind(self)
+        self.capture.set(cv2.CAP_PROP_POS_MSEC, 0)
+        self._lookahead = None
+        frame = None
+        for i in range(self.input_frame_index + 1):
+            success, frame = self.capture.read()
+            if not success or frame is None:
+                raise RuntimeError(f"An error occurred while reading frame at index {i}")
+        self.prev_gray = self._gray_on_device(frame)
+        self._prepared = False
+        self.prev_flow = None
+
+    def next(self) -> torch.Tensor:
+        success, frame = self._read_frame()
+        if frame is None or not success:
+            raise StopIteration
+        gray = self._gray_on_device(frame)
+        if self.direction not in (FlowSource.Direction.FORWARD, FlowSource.Direction.BACKWARD):
+            raise ValueError(f"Invalid flow direction '{self.direction}'")
+        if self.prev_gray is None:
+            raise ValueError("Missing reference frames")
+        forward = self.direction == FlowSource.Direction.FORWARD
+        engine = self._method_engine()
+        c = self.config
+        if c.method == CvFlowSource.Method.FARNEBACK:
+            if not self._prepared:
+                engine.prepare(self._slot, self.prev_gray)
+                self._prepared = True
+            cur = self._slot ^ 1
+            engine.prepare(cur, gray)
+            flow = engine.solve(self._slot, cur) if forward else engine.solve(cur, self._slot)
+            self._slot = cur
+        else:
+            left, right = (self.prev_gray, gray) if forward else (gray, self.prev_gray)
+            if c.method == CvFlowSource.Method.HORN_SCHUNCK:
+                prev = None if self.prev_flow is None else self.prev_flow.clone()
+                flow = engine(left, right, prev, c.hs_alpha, c.hs_iterations, c.hs_decay, c.hs_delta)
+            else:
+                flow = engine(left, right)
+        self.prev_gray = gray
+        return flow
+
+    def close(self):
+        self.capture.release()
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+
+
+_METHOD_NAMES = {"FARNEBACK": "farneback", "HORN_SCHUNCK": "horn-schunck", "LUKAS_KANADE": "lukas-kanade",
+                 "LITEFLOWNET": "liteflownet"}

@@ -4,11 +4,17 @@ Everything here runs on the current CUDA device and the current torch stream.  N
 has a CPU path; CPU tensors raise.
 """
 import ctypes as C
+import os
 
 import torch
 
 from . import _lib
 from ._lib import check, ptr, stream_ptr
+
+
+#: solve kernel variant used when none is requested: 0 fused streaming (float sums in smem),
+#: 1 unfused reference kernels, 2 fused streaming with double sums in smem
+DEFAULT_FB_VARIANT = 1
 
 
 def _cuda(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
@@ -35,9 +41,11 @@ class Farneback:
     """Device Farneback flow with the parameters of ``CvFlowConfig.fb_*`` (cv.py:275-281)."""
 
     def __init__(self, height, width, pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5,
-                 poly_sigma=1.2, flags=0, r_fp16=False, variant=0):
+                 poly_sigma=1.2, flags=0, r_fp16=False, variant=None):
         self.lib = _lib.load()
         self.h, self.w = int(height), int(width)
+        if variant is None:
+            variant = int(os.environ.get("TFB200_FB_VARIANT", DEFAULT_FB_VARIANT))
         self.variant = int(variant)
         self.handle = C.c_void_p()
         check(self.lib.tf_farneback_create(C.byref(self.handle), self.h, self.w, float(pyr_scale), int(levels),
