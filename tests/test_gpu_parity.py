@@ -187,7 +187,7 @@ def test_farneback_stages_match_restatement(params):
         assert np.abs(R - wantR).max() < 2e-4, (li, np.abs(R - wantR).max())
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("params", FB_PARAMS)
 @pytest.mark.parametrize("shape", [(135, 201), (480, 854)])
 def test_farneback_matches_cv2(shape, params, variant):
@@ -374,3 +374,17 @@ def test_no_cpu_fallback():
     from transflow_b200 import ops
     with pytest.raises(RuntimeError):
         ops.gray_from_bgr(torch.zeros((4, 4, 3), dtype=torch.uint8))
+
+
+@pytest.mark.parametrize("params", [dict(winsize=5, levels=2), dict(winsize=33, poly_n=3, poly_sigma=0.9),
+                                    dict(winsize=21, iterations=1, levels=0), dict(winsize=9, poly_n=10, poly_sigma=2.0)])
+def test_farneback_other_window_sizes(params):
+    """Every window radius is its own template instantiation of the fused kernel."""
+    from transflow_b200 import ops
+    h, w = 203, 310            # odd sizes: ragged tiles, unaligned rows
+    g0, g1 = clip_pair(h, w, seed=8)
+    want = F.farneback(g0, g1, **params)
+    for variant in (3, 1):
+        got = ops.Farneback(h, w, variant=variant, **params)(dev(g0), dev(g1)).cpu().numpy()
+        mean, mx = epe(got, want)
+        assert mean <= 0.01 and mx <= 0.1, (variant, mean, mx)

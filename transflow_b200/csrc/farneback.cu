@@ -364,6 +364,7 @@ __global__ void __launch_bounds__(256) k_fb_box_h_solve(const double* __restrict
 }
 
 #include "fb_iter.cuh"
+#include "fb_tile.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // C ABI
@@ -554,6 +555,9 @@ static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int var
                 }
                 if (!last) TF_LAUNCHED();
             }
+        } else if (variant == 3) {
+            if (int e = fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st))
+                return e;
         } else {
             if (int e = fb_iterate_fused<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest,
                                              variant == 2, finest, st))
@@ -569,7 +573,7 @@ extern "C" int tf_farneback_solve(tf_farneback* h, int slot_left, int slot_right
     TF_REQUIRE(h && flow, TF_ERR_INVALID_ARG, "tf_farneback_solve: null argument");
     TF_REQUIRE((slot_left == 0 || slot_left == 1) && (slot_right == 0 || slot_right == 1), TF_ERR_INVALID_ARG,
                "tf_farneback_solve: slots must be 0 or 1");
-    TF_REQUIRE(variant >= 0 && variant <= 2, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
+    TF_REQUIRE(variant >= 0 && variant <= 3, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
     TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_solve: flow must be 8-byte aligned");
     cudaStream_t st = as_stream(stream);
     float2* out = reinterpret_cast<float2*>(flow);

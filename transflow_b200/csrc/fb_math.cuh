@@ -20,27 +20,28 @@ __device__ __forceinline__ float load_r(const __half* p) { return __half2float(_
 
 __device__ __forceinline__ float fb_border(int d) { return d < 2 ? 0.14f : 0.4472f; }
 
-// FarnebackUpdateMatrices for one pixel: R0 at (x, y), R1 sampled bilinearly at (x+dx, y+dy)
-// (falls back to R0 only when the sample leaves the image), 5-px border attenuation.
-// R planes are ordered (d/dy, d/dx, yy, xx, xy), each w*h elements.
+// FarnebackUpdateMatrices for one pixel: R0 at (x, y) (already loaded into a[5]), R1 sampled
+// bilinearly at (x+dx, y+dy) (falls back to R0 only when the sample leaves the image), 5-px border
+// attenuation.  R planes are ordered (d/dy, d/dx, yy, xx, xy), each w*h elements.
 template <typename RT>
-__device__ __forceinline__ void fb_update_matrix(const RT* __restrict__ R0, const RT* __restrict__ R1, size_t plane,
-                                                 int w, int h, int x, int y, float2 f, float* m) {
-    size_t at = (size_t)y * w + x;
-    float a0 = load_r(R0 + at), a1 = load_r(R0 + plane + at), a2 = load_r(R0 + 2 * plane + at),
-          a3 = load_r(R0 + 3 * plane + at), a4 = load_r(R0 + 4 * plane + at);
+__device__ __forceinline__ void fb_load_r0(const RT* __restrict__ R0, size_t plane, size_t at, float* a) {
+#pragma unroll
+    for (int c = 0; c < 5; c++) a[c] = load_r(R0 + c * plane + at);
+}
+
+template <typename RT>
+__device__ __forceinline__ void fb_update_matrix_pre(const float* a, const RT* __restrict__ R1, size_t plane, int w,
+                                                     int h, int x, int y, float2 f, float* m) {
     float dx = f.x, dy = f.y;
     float fx = (float)x + dx, fy = (float)y + dy;
-    float flx = floorf(fx), fly = floorf(fy);
-    // cvFloor of a float: values beyond int range are treated as outside
-    int x1 = (fabsf(flx) < 1e9f) ? (int)flx : -1, y1 = (fabsf(fly) < 1e9f) ? (int)fly : -1;
-    fx -= flx;
-    fy -= fly;
+    // cvFloor; the float->int conversion saturates, so absurd displacements land outside the image
+    int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
+    fx -= (float)x1;
+    fy -= (float)y1;
     float r2, r3, r4, r5, r6;
     if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
         float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-        size_t q = (size_t)y1 * w + x1;
-        const RT* p = R1 + q;
+        const RT* p = R1 + ((size_t)y1 * w + x1);
         r2 = a00 * load_r(p) + a01 * load_r(p + 1) + a10 * load_r(p + w) + a11 * load_r(p + w + 1);
         p += plane;
         r3 = a00 * load_r(p) + a01 * load_r(p + 1) + a10 * load_r(p + w) + a11 * load_r(p + w + 1);
@@ -50,17 +51,17 @@ __device__ __forceinline__ void fb_update_matrix(const RT* __restrict__ R0, cons
         r5 = a00 * load_r(p) + a01 * load_r(p + 1) + a10 * load_r(p + w) + a11 * load_r(p + w + 1);
         p += plane;
         r6 = a00 * load_r(p) + a01 * load_r(p + 1) + a10 * load_r(p + w) + a11 * load_r(p + w + 1);
-        r4 = (a2 + r4) * 0.5f;
-        r5 = (a3 + r5) * 0.5f;
-        r6 = (a4 + r6) * 0.25f;
+        r4 = (a[2] + r4) * 0.5f;
+        r5 = (a[3] + r5) * 0.5f;
+        r6 = (a[4] + r6) * 0.25f;
     } else {
         r2 = r3 = 0.f;
-        r4 = a2;
-        r5 = a3;
-        r6 = a4 * 0.5f;
+        r4 = a[2];
+        r5 = a[3];
+        r6 = a[4] * 0.5f;
     }
-    r2 = (a0 - r2) * 0.5f;
-    r3 = (a1 - r3) * 0.5f;
+    r2 = (a[0] - r2) * 0.5f;
+    r3 = (a[1] - r3) * 0.5f;
     r2 += r4 * dy + r6 * dx;
     r3 += r6 * dy + r5 * dx;
     if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
@@ -73,6 +74,14 @@ __device__ __forceinline__ void fb_update_matrix(const RT* __restrict__ R0, cons
     m[2] = r5 * r5 + r6 * r6;  // G(2,2)
     m[3] = r4 * r2 + r6 * r3;  // h(1)
     m[4] = r6 * r2 + r5 * r3;  // h(2)
+}
+
+template <typename RT>
+__device__ __forceinline__ void fb_update_matrix(const RT* __restrict__ R0, const RT* __restrict__ R1, size_t plane,
+                                                 int w, int h, int x, int y, float2 f, float* m) {
+    float a[5];
+    fb_load_r0<RT>(R0, plane, (size_t)y * w + x, a);
+    fb_update_matrix_pre<RT>(a, R1, plane, w, h, x, y, f, m);
 }
 
 // 2x2 solve of FarnebackUpdateFlow_Blur, in double like cv2 (the determinant cancels).

@@ -14,7 +14,7 @@ from ._lib import check, ptr, stream_ptr
 
 #: solve kernel variant used when none is requested: 0 fused streaming (float sums in smem),
 #: 1 unfused reference kernels, 2 fused streaming with double sums in smem
-DEFAULT_FB_VARIANT = 1
+DEFAULT_FB_VARIANT = 3
 
 
 def _cuda(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
