@@ -1,0 +1,244 @@
+"""Frame-pair sharding across the GPUs of one box (one process per GPU).
+
+Flow estimation of pair t is independent of pair t+-1 (Farneback with fb_flags = 0, PyrLK,
+Horn-Schunck with hs_decay = 0), so it shards by CHUNKS of K consecutive pairs: a rank that
+owns a chunk prepares K + 1 frames and reuses every frame's pyramid / polynomial expansion for
+two pairs.  Accumulate + remap is a strict recurrence (``data_t = f(data_{t-1}, flow_t)``) and
+runs on rank 0 only, in frame order.  There is no collective on the data path: the only
+exchange is the point-to-point hand-off of finished flow fields to rank 0
+(``torch.distributed`` send/recv = NCCL over NVLink on the GPU box, gloo in the CPU tests).
+
+The stream is cut into rounds.  In every round each producer rank r >= 1 owns ``q`` chunks and
+rank 0 owns ``c0 <= q`` chunks, where ``c0`` balances rank 0's extra accumulate work (see
+``plan_round``): with F = cost of one flow and A = cost of one accumulate+remap, rank 0 finishes
+a round together with the producers when ``c0 = q * (1 - (N - 1) * A/F) / (1 + A/F)``.
+"""
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def plan_round(world: int, q: int, flow_ms: float, accumulate_ms: float) -> list:
+    """Chunks per rank in one round: ``[c0, q, q, ...]``.
+
+    Rank 0 spends ``c0 * F + T * A`` per round (T = c0 + (world - 1) * q chunks), a producer
+    ``q * F``.  Balancing gives ``c0 = q * (1 - (world - 1) * a) / (1 + a)`` with ``a = A / F``,
+    clamped to ``[0, q]`` and rounded down (rank 0 must never be the late one).
+    """
+    if world == 1:
+        return [q]
+    a = accumulate_ms / max(flow_ms, 1e-9)
+    c0 = q * (1.0 - (world - 1) * a) / (1.0 + a)
+    c0 = int(max(0, min(q, np.floor(c0 + 1e-9))))
+    return [c0] + [q] * (world - 1)
+
+
+def round_slots(counts: list) -> list:
+    """Owner rank of every chunk slot of a round, in stream order (rank 0's chunks first)."""
+    owners = []
+    for rank, c in enumerate(counts):
+        owners += [rank] * c
+    return owners
+
+
+class ShardedFlowStream:
+    """Drives one rank of the sharded pipeline.
+
+    ``estimate_chunk(first_pair, n_pairs)`` -> list of post-processed flow tensors (producer side);
+    ``accumulate(flow)`` consumes flows strictly in frame order (rank 0 only).
+    Works with any ``torch.distributed`` backend: tensors only need to live on the device the
+    backend moves (CUDA for nccl, CPU for gloo).
+    """
+
+    def __init__(self, rank, world, chunk_pairs, counts, estimate_chunk, accumulate, flow_shape, device,
+                 group=None):
+        self.rank, self.world, self.k = rank, world, chunk_pairs
+        self.counts = list(counts)
+        self.owners = round_slots(self.counts)
+        self.cpr = len(self.owners)
+        self.estimate_chunk, self.accumulate = estimate_chunk, accumulate
+        self.flow_shape, self.device, self.group = tuple(flow_shape), device, group
+        self.frames_accumulated = 0
+        # rank 0 keeps one receive buffer per (remote slot, pair) of a round, double-buffered by round
+        self._recv = {}
+
+    @property
+    def frames_per_round(self) -> int:
+        return self.cpr * self.k
+
+    def _recv_buffers(self, parity: int, slot: int):
+        key = (parity, slot)
+        if key not in self._recv:
+            self._recv[key] = [torch.empty(self.flow_shape, dtype=torch.float32, device=self.device)
+                               for _ in range(self.k)]
+        return self._recv[key]
+
+    def run_round(self, round_index: int):
+        base_chunk = round_index * self.cpr
+        parity = round_index & 1
+        if self.rank == 0:
+            # post every receive of the round first so transfers overlap rank 0's own estimation
+            pending = {}
+            for slot, owner in enumerate(self.owners):
+                if owner != 0:
+                    bufs = self._recv_buffers(parity, slot)
+                    pending[slot] = [dist.irecv(b, src=owner, group=self.group) for b in bufs]
+            for slot, owner in enumerate(self.owners):
+                if owner == 0:
+                    flows = self.estimate_chunk((base_chunk + slot) * self.k, self.k)
+                else:
+                    for w in pending[slot]:
+                        w.wait()
+                    flows = self._recv_buffers(parity, slot)
+                for f in flows:
+                    self.accumulate(f)
+                    self.frames_accumulated += 1
+        else:
+            works, keep = [], []
+            for slot, owner in enumerate(self.owners):
+                if owner == self.rank:
+                    flows = [f.contiguous() for f in self.estimate_chunk((base_chunk + slot) * self.k, self.k)]
+                    keep.append(flows)                      # alive until the sends have completed
+                    works += [dist.isend(f, dst=0, group=self.group) for f in flows]
+            for w in works:
+                w.wait()
+
+
+# ------------------------------------------------------------------------------------------------
+# bench.py --gpus N (N > 1): the C3 workload sharded over N ranks
+# ------------------------------------------------------------------------------------------------
+def bench_sharded(args, rank, world, local):
+    import json
+
+    from . import _lib, ops
+    from .compositor import Compositor
+    from .compositor.pixmap_source_interface import PixmapSourceInterface, StillQueue
+    from .config import LayerConfig
+    import bench as B
+
+    H, W = args.height, args.width
+    K, Q = 4, 4
+    clip, mask, pixmap = B.build_workload(H, W, B.N_DISTINCT, seed=0)
+    frames_dev = torch.from_numpy(clip).cuda()
+    frames_pinned = torch.from_numpy(clip).pin_memory()
+    io = {"host": False}
+
+    def frame(idx):
+        i = B.frame_order(idx, B.N_DISTINCT)
+        return frames_pinned[i].cuda(non_blocking=True) if io["host"] else frames_dev[i]
+    fb = ops.Farneback(H, W)
+    post = ops.PostProcess(H, W, forward=True)
+    gray = torch.empty((H, W), dtype=torch.uint8, device="cuda")
+
+    def estimate_chunk(first_pair, n_pairs):
+        """K consecutive pairs: K + 1 prepares (one extra per chunk), K solves + post-processes."""
+        slot = 0
+        ops.gray_from_bgr(frame(first_pair), gray)
+        fb.prepare(slot, gray)
+        flows = []
+        for i in range(n_pairs):
+            cur = slot ^ 1
+            ops.gray_from_bgr(frame(first_pair + i + 1), gray)
+            fb.prepare(cur, gray)
+            flow = fb.solve(slot, cur)          # forward: (prev, cur)
+            flows.append(post(flow))
+            slot = cur
+        return flows
+
+    comp = None
+    rgb = None
+    if rank == 0:
+        mask_png = B.write_mask_png(mask, "shard")
+        comp = Compositor.from_args(H, W, [LayerConfig(0, "moveref", reset_mode="random", reset_random_factor=0.5,
+                                                       reset_mask=mask_png)], background_color=B.BG)
+        comp.set_sources({0: [PixmapSourceInterface(StillQueue(torch.from_numpy(pixmap).cuda()),
+                                                    np.ones((H, W), bool))]})
+        rgb = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
+        rgb_host = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+
+    def accumulate(flow):
+        comp.step(flow, rgb)
+        if io["host"]:
+            rgb_host.copy_(rgb, non_blocking=True)
+
+    # calibrate F (flow per pair) and A (accumulate per frame) on rank 0, share the plan
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    estimate_chunk(0, K)
+    f_ms = timed(lambda: estimate_chunk(0, K), 2) / K
+    plan = torch.zeros(2, dtype=torch.float64, device="cuda")
+    if rank == 0:
+        fl = estimate_chunk(0, 1)[0]
+        accumulate(fl)
+        a_ms = timed(lambda: accumulate(fl), 4)
+        plan[0], plan[1] = f_ms, a_ms
+    dist.broadcast(plan, src=0)
+    f_ms, a_ms = float(plan[0]), float(plan[1])
+    counts = plan_round(world, Q, f_ms, a_ms)
+    stream = ShardedFlowStream(rank, world, K, counts, estimate_chunk, accumulate, (H, W, 2), "cuda")
+
+    def timed_rounds(first):
+        for r in range(first, first + args.warmup):
+            stream.run_round(r)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for r in range(first + args.warmup, first + args.warmup + args.steps):
+            stream.run_round(r)
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t
+
+    # end to end first: every frame enters from pinned host memory, every RGB frame returns to it
+    io["host"] = True
+    ms_e2e = timed_rounds(0)
+    io["host"] = False
+    sampler = B.ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ms = timed_rounds(args.warmup + args.steps)
+    launches = torch.tensor([_lib.launch_count() - launches0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        clocks = sampler.stop()
+        frames = args.steps * stream.frames_per_round
+        fps = frames / (float(ms) / 1000.0)
+        peak, peak_src = B.measured_peak_gbs()
+        n_px = H * W
+        frame_bytes = fb.algorithmic_bytes(True) + (24.0 + 50.0) * n_px + 4.0 * n_px
+        line = {
+            "metric": "frames/sec at 4K (flow+accumulate+remap)", "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms) / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(B.workload_config(args), sharding=f"chunks of {K} pairs; per round {counts} chunks per rank "
+                           f"(rank 0 also runs the sequential accumulate+remap); flows sent to rank 0 with NCCL "
+                           f"send/recv", frames_per_step=stream.frames_per_round,
+                           calibrated_ms={"flow_per_pair": f_ms, "accumulate_per_frame": a_ms}),
+            "roofline": None,
+            "e2e": {"value": frames / (float(ms_e2e) / 1000.0), "unit": "frames/s",
+                    "h2d_bytes_per_step": int(stream.frames_per_round * n_px * 3 * (K + 1) / K),
+                    "d2h_bytes_per_step": int(stream.frames_per_round * n_px * 3),
+                    "api": "sharded stream: pinned BGR frames H2D on every rank, RGB frames D2H on rank 0"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "pipeline_hbm_frac": frame_bytes * fps / 1e9 / (peak * world),
+            "exchange_bytes_per_step": int(sum(counts[1:]) * K * n_px * 8),
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+    return 0
