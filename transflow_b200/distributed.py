@@ -6,16 +6,16 @@ owns a chunk prepares K + 1 frames and reuses every frame's pyramid / polynomial
 two pairs.  Accumulate + remap is a strict recurrence (``data_t = f(data_{t-1}, flow_t)``) and
 runs on rank 0 only, in frame order.  There is no collective on the data path: the only
 exchange is the point-to-point hand-off of finished flow fields to rank 0
-(``torch.distributed`` send/recv = NCCL over NVLink on the GPU box, gloo in the CPU tests).
+(``torch.distributed`` batched send/recv = NCCL over NVLink on the GPU box, gloo in the CPU
+tests).
 
 The stream is cut into rounds.  In every round each producer rank r >= 1 owns ``q`` chunks and
 rank 0 owns ``c0 <= q`` chunks, where ``c0`` balances rank 0's extra accumulate work (see
 ``plan_round``): with F = cost of one flow and A = cost of one accumulate+remap, rank 0 finishes
 a round together with the producers when ``c0 = q * (1 - (N - 1) * A/F) / (1 + A/F)``.
+Rank 0 posts the receives of round j + 1 before it consumes round j (two buffer sets), so
+producers run one round ahead of the accumulator instead of stalling on it.
 """
-import os
-import time
-
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -62,8 +62,7 @@ class ShardedFlowStream:
         self.estimate_chunk, self.accumulate = estimate_chunk, accumulate
         self.flow_shape, self.device, self.group = tuple(flow_shape), device, group
         self.frames_accumulated = 0
-        # rank 0 keeps one receive buffer per (remote slot, pair) of a round, double-buffered by round
-        self._recv = {}
+        self._recv = {}      # (round parity, slot) -> K receive buffers
 
     @property
     def frames_per_round(self) -> int:
@@ -76,35 +75,87 @@ class ShardedFlowStream:
                                for _ in range(self.k)]
         return self._recv[key]
 
-    def run_round(self, round_index: int):
-        base_chunk = round_index * self.cpr
-        parity = round_index & 1
+    def _post_receives(self, round_index: int) -> dict:
+        """One batched P2P group per remote chunk slot of the round -> {slot: [work, ...]}."""
+        pending = {}
+        for slot, owner in enumerate(self.owners):
+            if owner != 0:
+                bufs = self._recv_buffers(round_index & 1, slot)
+                ops = [dist.P2POp(dist.irecv, b, owner, self.group) for b in bufs]
+                pending[slot] = dist.batch_isend_irecv(ops)
+        return pending
+
+    def run(self, first_round: int, n_rounds: int):
+        """Process rounds [first_round, first_round + n_rounds)."""
+        if n_rounds <= 0:
+            return
+        last = first_round + n_rounds - 1
         if self.rank == 0:
-            # post every receive of the round first so transfers overlap rank 0's own estimation
-            pending = {}
-            for slot, owner in enumerate(self.owners):
-                if owner != 0:
-                    bufs = self._recv_buffers(parity, slot)
-                    pending[slot] = [dist.irecv(b, src=owner, group=self.group) for b in bufs]
-            for slot, owner in enumerate(self.owners):
-                if owner == 0:
-                    flows = self.estimate_chunk((base_chunk + slot) * self.k, self.k)
-                else:
-                    for w in pending[slot]:
-                        w.wait()
-                    flows = self._recv_buffers(parity, slot)
-                for f in flows:
-                    self.accumulate(f)
-                    self.frames_accumulated += 1
+            pending = self._post_receives(first_round)
+            for j in range(first_round, last + 1):
+                upcoming = self._post_receives(j + 1) if j < last else {}
+                base_chunk = j * self.cpr
+                for slot, owner in enumerate(self.owners):
+                    if owner == 0:
+                        flows = self.estimate_chunk((base_chunk + slot) * self.k, self.k)
+                    else:
+                        for w in pending[slot]:
+                            w.wait()
+                        flows = self._recv_buffers(j & 1, slot)
+                    for f in flows:
+                        self.accumulate(f)
+                        self.frames_accumulated += 1
+                pending = upcoming
         else:
-            works, keep = [], []
-            for slot, owner in enumerate(self.owners):
-                if owner == self.rank:
-                    flows = [f.contiguous() for f in self.estimate_chunk((base_chunk + slot) * self.k, self.k)]
-                    keep.append(flows)                      # alive until the sends have completed
-                    works += [dist.isend(f, dst=0, group=self.group) for f in flows]
-            for w in works:
-                w.wait()
+            in_flight = []       # (works, tensors) of the previous round: bounded look-ahead
+            for j in range(first_round, last + 1):
+                base_chunk = j * self.cpr
+                works, keep = [], []
+                for slot, owner in enumerate(self.owners):
+                    if owner == self.rank:
+                        flows = [f.contiguous() for f in self.estimate_chunk((base_chunk + slot) * self.k, self.k)]
+                        keep.append(flows)              # alive until the sends have completed
+                        ops = [dist.P2POp(dist.isend, f, 0, self.group) for f in flows]
+                        works += dist.batch_isend_irecv(ops)
+                in_flight.append((works, keep))
+                if len(in_flight) > 1:
+                    for w in in_flight.pop(0)[0]:
+                        w.wait()
+            for works, _ in in_flight:
+                for w in works:
+                    w.wait()
+
+    def run_round(self, round_index: int):
+        self.run(round_index, 1)
+
+
+class _HostFrameFeeder:
+    """Pinned host clip -> device frames through a side stream with one frame of look-ahead."""
+
+    def __init__(self, frames_pinned, order_fn):
+        self.frames, self.order = frames_pinned, order_fn
+        self.stream = torch.cuda.Stream()
+        self.cache = {}
+
+    def _start(self, idx):
+        if idx in self.cache:
+            return
+        with torch.cuda.stream(self.stream):
+            dev = self.frames[self.order(idx)].cuda(non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.cache[idx] = (dev, ev)
+
+    def get(self, idx):
+        self._start(idx)
+        dev, ev = self.cache.pop(idx)
+        self._start(idx + 1)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        dev.record_stream(cur)
+        for stale in [k for k in self.cache if k != idx + 1]:
+            del self.cache[stale]
+        return dev
 
 
 # ------------------------------------------------------------------------------------------------
@@ -123,12 +174,11 @@ def bench_sharded(args, rank, world, local):
     K, Q = 4, 4
     clip, mask, pixmap = B.build_workload(H, W, B.N_DISTINCT, seed=0)
     frames_dev = torch.from_numpy(clip).cuda()
-    frames_pinned = torch.from_numpy(clip).pin_memory()
+    feeder = _HostFrameFeeder(torch.from_numpy(clip).pin_memory(), lambda i: B.frame_order(i, B.N_DISTINCT))
     io = {"host": False}
 
     def frame(idx):
-        i = B.frame_order(idx, B.N_DISTINCT)
-        return frames_pinned[i].cuda(non_blocking=True) if io["host"] else frames_dev[i]
+        return feeder.get(idx) if io["host"] else frames_dev[B.frame_order(idx, B.N_DISTINCT)]
     fb = ops.Farneback(H, W)
     post = ops.PostProcess(H, W, forward=True)
     gray = torch.empty((H, W), dtype=torch.uint8, device="cuda")
@@ -149,20 +199,33 @@ def bench_sharded(args, rank, world, local):
         return flows
 
     comp = None
-    rgb = None
     if rank == 0:
         mask_png = B.write_mask_png(mask, "shard")
         comp = Compositor.from_args(H, W, [LayerConfig(0, "moveref", reset_mode="random", reset_random_factor=0.5,
                                                        reset_mask=mask_png)], background_color=B.BG)
         comp.set_sources({0: [PixmapSourceInterface(StillQueue(torch.from_numpy(pixmap).cuda()),
                                                     np.ones((H, W), bool))]})
-        rgb = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
-        rgb_host = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+        rgb = [torch.empty((H, W, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        rgb_host = [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        down = torch.cuda.Stream()
+        copied = [None, None]
+        count = {"n": 0}
 
     def accumulate(flow):
-        comp.step(flow, rgb)
+        k = count["n"] & 1
+        count["n"] += 1
+        if io["host"] and copied[k] is not None:
+            torch.cuda.current_stream().wait_event(copied[k])   # the D2H out of this buffer is done
+        comp.step(flow, rgb[k])
         if io["host"]:
-            rgb_host.copy_(rgb, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(down):
+                down.wait_event(ready)
+                rgb_host[k].copy_(rgb[k], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(down)
+            copied[k] = ev
 
     # calibrate F (flow per pair) and A (accumulate per frame) on rank 0, share the plan
     def timed(fn, n):
@@ -188,15 +251,13 @@ def bench_sharded(args, rank, world, local):
     stream = ShardedFlowStream(rank, world, K, counts, estimate_chunk, accumulate, (H, W, 2), "cuda")
 
     def timed_rounds(first):
-        for r in range(first, first + args.warmup):
-            stream.run_round(r)
+        stream.run(first, args.warmup)
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for r in range(first + args.warmup, first + args.warmup + args.steps):
-            stream.run_round(r)
+        stream.run(first + args.warmup, args.steps)
         e1.record()
         torch.cuda.synchronize()
         dist.barrier()
@@ -227,8 +288,8 @@ def bench_sharded(args, rank, world, local):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms) / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(B.workload_config(args), sharding=f"chunks of {K} pairs; per round {counts} chunks per rank "
-                           f"(rank 0 also runs the sequential accumulate+remap); flows sent to rank 0 with NCCL "
-                           f"send/recv", frames_per_step=stream.frames_per_round,
+                           f"(rank 0 also runs the sequential accumulate+remap); flows sent to rank 0 with batched "
+                           f"NCCL send/recv, receives posted one round ahead", frames_per_step=stream.frames_per_round,
                            calibrated_ms={"flow_per_pair": f_ms, "accumulate_per_frame": a_ms}),
             "roofline": None,
             "e2e": {"value": frames / (float(ms_e2e) / 1000.0), "unit": "frames/s",
