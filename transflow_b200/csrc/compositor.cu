@@ -57,9 +57,10 @@ struct LayerParams {
     int do_introduce;
 };
 
-// ---- Philox4x32-10 (counter = pixel, key = seed ^ frame): throughput-mode reset draws ------
-__device__ __forceinline__ double philox_uniform53(uint64_t seed, uint64_t frame, uint32_t pixel) {
-    uint32_t c0 = pixel, c1 = (uint32_t)frame, c2 = (uint32_t)(frame >> 32), c3 = 0x7f4a7c15u;
+// ---- Philox4x32-10 (counter = pixel pair, key = seed; frame in the counter): throughput-mode reset
+// draws.  One call yields 128 bits = two 53-bit uniforms, so a pixel pair shares one evaluation.
+__device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t frame, uint32_t ctr) {
+    uint32_t c0 = ctr, c1 = (uint32_t)frame, c2 = (uint32_t)(frame >> 32), c3 = 0x7f4a7c15u;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
     for (int r = 0; r < 10; r++) {
@@ -69,8 +70,14 @@ __device__ __forceinline__ double philox_uniform53(uint64_t seed, uint64_t frame
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ double philox_uniform53(uint64_t seed, uint64_t frame, uint32_t pixel) {
+    uint4 r = philox4x32_10(seed, frame, pixel >> 1);
+    uint32_t a = (pixel & 1) ? r.z : r.x, b = (pixel & 1) ? r.w : r.y;
     // same 53-bit construction as numpy's random_sample: (a >> 5) * 2^26 + (b >> 6)
-    return ((double)(c0 >> 5) * 67108864.0 + (double)(c1 >> 6)) * (1.0 / 9007199254740992.0);
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 
 __device__ __forceinline__ int wrap_index(int q, int n, int p, int* err) {
@@ -239,38 +246,93 @@ __device__ __forceinline__ void composite4(const LayerParams& P, int p0, int cou
 }
 
 // ---- moveref / sum: move (or add) -> reset -> remap -> [render + composite] -----------------
+// The four pixels of a thread are processed stage by stage (all flow loads, then all record
+// gathers, then all pixmap gathers), so a thread exposes three memory round trips instead of twelve.
 template <int KIND>
 __global__ void __launch_bounds__(256) k_reference_layer(LayerParams P) {
-    int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (p0 >= P.n) return;
-    int count = min(4, P.n - p0);
+    const int count = min(4, P.n - p0);
+    int pk[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) pk[k] = min(p0 + k, P.n - 1);  // tail lanes recompute the last pixel, stores are guarded
+
+    // stage 1: flow
+    float2 f[4];
+    if (count == 4 && (reinterpret_cast<uintptr_t>(P.flow) & 15) == 0) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(P.flow + p0));
+        float4 b = __ldg(reinterpret_cast<const float4*>(P.flow + p0) + 1);
+        f[0] = make_float2(a.x, a.y); f[1] = make_float2(a.z, a.w);
+        f[2] = make_float2(b.x, b.y); f[3] = make_float2(b.z, b.w);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) f[k] = __ldg(P.flow + pk[k]);
+    }
+    // stage 2: records (own + source) and per-pixel planes
+    int4 rec[4];
+    uchar4 old_px[4];
+    if (KIND == TF_LAYER_MOVEREF) {
+        int q[4], off[4];
+        int4 rp[4], rq[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            off[k] = __float2int_rn(f[k].y) * P.w + __float2int_rn(f[k].x);  // numpy.round = half-even
+            q[k] = off[k] != 0 ? wrap_index(pk[k] + off[k], P.n, pk[k], P.err) : pk[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) rp[k] = __ldg(P.old + pk[k]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) rq[k] = off[k] != 0 ? __ldg(P.old + q[k]) : rp[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            // MovementLayer._update_move (movement.py:25-60)
+            bool src_alpha = rq[k].z != 0;
+            bool ok = off[k] != 0 && (P.mask_src == nullptr || P.mask_src[q[k]] != 0) &&
+                      (P.mask_dst == nullptr || P.mask_dst[pk[k]] != 0);
+            if (!P.cfg.transparent_pixels_can_move) ok = ok && src_alpha;
+            if (!P.cfg.pixels_can_move_to_empty_spot) ok = ok && rp[k].z != 0;
+            if (!P.cfg.pixels_can_move_to_filled_spot) ok = ok && rp[k].z == 0;
+            rec[k] = ok ? rq[k] : rp[k];
+            if (P.cfg.moving_pixels_leave_empty_spot && P.vacated[pk[k]] == P.stamp) rec[k].z = 0;
+            if (ok && (!P.cfg.transparent_pixels_can_move || src_alpha)) rec[k].z = 1;
+        }
+    } else {
+        // SumLayer._update_sum (sum.py:9-10): x is added to the ROW index (quirk Q8); in place, so
+        // plain loads (not the read-only path)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            rec[k] = P.out[pk[k]];
+            rec[k].x += (int)floorf(f[k].x);
+            rec[k].y += (int)floorf(f[k].y);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) old_px[k] = P.rgba[pk[k]];
+    // stage 3: reset + remap
     uchar4 px[4];
+    {
+        int y = p0 / P.w, x = p0 - y * P.w;   // one division per thread; the other pixels step from it
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            apply_reset(P, pk[k], y, x, rec[k]);
+            if (k + 1 < count && ++x == P.w) {
+                x = 0;
+                y++;
+            }
+        }
+    }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        if (k >= count) break;
-        int p = p0 + k;
-        int y = p / P.w, x = p - y * P.w;
-        int4 rec;
-        if (KIND == TF_LAYER_MOVEREF) {
-            // MovementLayer.update (movement.py:20-60)
-            MoveDecision d = decide_move<0>(P, p, 1);
-            rec = __ldg(P.old + (d.target ? d.q : p));
-            if (P.cfg.moving_pixels_leave_empty_spot && P.vacated[p] == P.stamp) rec.z = 0;
-            if (d.filled_target) rec.z = 1;
-        } else {
-            // SumLayer._update_sum (sum.py:9-10): x is added to the ROW index (quirk Q8)
-            float2 f = __ldg(P.flow + p);
-            rec = P.out[p];  // in place (old == out): plain load, not the read-only path
-            rec.x += (int)floorf(f.x);
-            rec.y += (int)floorf(f.y);
-        }
-        apply_reset(P, p, y, x, rec);
-        P.out[p] = rec;
-        uchar4 c = remap_pixel(P, rec, P.rgba[p]);
-        if (P.rgb) c.w = alpha_mask_u8(P.mask_alpha, p, c.w);
-        P.rgba[p] = c;
-        px[k] = c;
+        px[k] = remap_pixel(P, rec[k], old_px[k]);
+        if (P.rgb) px[k].w = alpha_mask_u8(P.mask_alpha, pk[k], px[k].w);
     }
+    // stage 4: stores
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (k < count) {
+            P.out[p0 + k] = rec[k];
+            P.rgba[p0 + k] = px[k];
+        }
     composite4(P, p0, count, px);
 }
 

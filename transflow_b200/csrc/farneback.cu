@@ -211,19 +211,75 @@ __global__ void __launch_bounds__(256) k_fb_vpass(const float* __restrict__ T, f
 // The tile's first pixel is subtracted before accumulation: the five stored coefficients are
 // invariant to a constant offset (the fit of a constant has zero derivative terms), and the
 // smaller magnitudes keep fp32 accumulation at the accuracy of cv2's double accumulators.
-template <int N, typename RT>
-__global__ void __launch_bounds__(256) k_fb_polyexp(const float* __restrict__ img, RT* __restrict__ R, int w, int h,
-                                                    PolyCoef pc) {
+// FUSE3: the pyramid image of a level with identity resize and a 3-tap Gaussian (the finest level)
+// is computed on the fly from the gray frame while the tile is loaded (row filter then column
+// filter, BORDER_REFLECT_101, same rounding order as the separate passes) and also written out.
+__device__ __forceinline__ float fb_blur3(const uint8_t* __restrict__ gray, int x, int y, int w, int h, float k0,
+                                          float k1) {
+    int xl = x > 0 ? x - 1 : (w > 1 ? 1 : 0), xr = x < w - 1 ? x + 1 : (w > 1 ? w - 2 : 0);
+    int yu = y > 0 ? y - 1 : (h > 1 ? 1 : 0), yd = y < h - 1 ? y + 1 : (h > 1 ? h - 2 : 0);
+    const uint8_t* r0 = gray + (size_t)yu * w;
+    const uint8_t* r1 = gray + (size_t)y * w;
+    const uint8_t* r2 = gray + (size_t)yd * w;
+    float h0 = fmaf(k0, (float)r0[xr], fmaf(k1, (float)r0[x], k0 * (float)r0[xl]));
+    float h1 = fmaf(k0, (float)r1[xr], fmaf(k1, (float)r1[x], k0 * (float)r1[xl]));
+    float h2 = fmaf(k0, (float)r2[xr], fmaf(k1, (float)r2[x], k0 * (float)r2[xl]));
+    return fmaf(k0, h2, fmaf(k1, h1, k0 * h0));
+}
+
+template <int N, typename RT, bool FUSE3>
+__global__ void __launch_bounds__(256) k_fb_polyexp(const float* __restrict__ img, const uint8_t* __restrict__ gray,
+                                                    float* __restrict__ img_out, RT* __restrict__ R, int w, int h,
+                                                    PolyCoef pc, float k0, float k1) {
     constexpr int TX = 64, TY = 16, SW = TX + 2 * N, SH = TY + 2 * N, SP = SW + 1;
     __shared__ float sI[SH * SP];
     __shared__ float sV[3][TY * SP];
     int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
     int tid = threadIdx.x;
-    float c0 = __ldg(img + (size_t)min(y0, h - 1) * w + min(x0, w - 1));
-    for (int i = tid; i < SH * SW; i += 256) {
+    // FUSE3 fast path for tiles whose halo'd footprint lies inside the frame: the gray tile is staged
+    // in shared memory as float once (one conversion per byte) and the 3x3 blur reads it from there
+    constexpr int GP = SW + 3;  // pitch of the staged gray tile (SW + 2 columns)
+    const bool interior = FUSE3 && x0 - N - 1 >= 0 && y0 - N - 1 >= 0 && x0 + TX + N + 1 <= w && y0 + TY + N + 1 <= h;
+    if (interior) {
+        static_assert((SH + 2) * GP <= 3 * TY * SP, "staged gray tile must fit in the sV scratch");
+        float* sG = &sV[0][0];
+        for (int i = tid; i < (SH + 2) * (SW + 2); i += 256) {
+            int r = i / (SW + 2), c = i - r * (SW + 2);
+            sG[r * GP + c] = (float)__ldg(gray + (size_t)(y0 - N - 1 + r) * w + (x0 - N - 1 + c));
+        }
+        __syncthreads();
+        auto blur = [&](int ly, int lx) {
+            const float* g = sG + ly * GP + lx;  // top-left of the 3x3 neighbourhood of I(ly, lx)
+            float h0 = fmaf(k0, g[2], fmaf(k1, g[1], k0 * g[0]));
+            float h1 = fmaf(k0, g[GP + 2], fmaf(k1, g[GP + 1], k0 * g[GP]));
+            float h2 = fmaf(k0, g[2 * GP + 2], fmaf(k1, g[2 * GP + 1], k0 * g[2 * GP]));
+            return fmaf(k0, h2, fmaf(k1, h1, k0 * h0));
+        };
+        float c0i = blur(N, N);
+        for (int i = tid; i < SH * SW; i += 256) {
+            int ly = i / SW, lx = i - ly * SW;
+            float v = blur(ly, lx);
+            if (ly >= N && ly < N + TY && lx >= N && lx < N + TX)
+                img_out[(size_t)(y0 + ly - N) * w + (x0 + lx - N)] = v;
+            sI[ly * SP + lx] = v - c0i;
+        }
+    }
+    float c0 = interior ? 0.f
+               : FUSE3  ? fb_blur3(gray, min(x0, w - 1), min(y0, h - 1), w, h, k0, k1)
+                        : __ldg(img + (size_t)min(y0, h - 1) * w + min(x0, w - 1));
+    for (int i = tid; i < (interior ? 0 : SH * SW); i += 256) {
         int ly = i / SW, lx = i - ly * SW;
         int gy = clampi(y0 + ly - N, 0, h - 1), gx = clampi(x0 + lx - N, 0, w - 1);
-        sI[ly * SP + lx] = __ldg(img + (size_t)gy * w + gx) - c0;
+        float v;
+        if (FUSE3) {
+            v = fb_blur3(gray, gx, gy, w, h, k0, k1);
+            // interior of the tile: publish the pyramid image (debug hook / other consumers)
+            if (ly >= N && ly < N + TY && lx >= N && lx < N + TX && y0 + ly - N < h && x0 + lx - N < w)
+                img_out[(size_t)gy * w + gx] = v;
+        } else {
+            v = __ldg(img + (size_t)gy * w + gx);
+        }
+        sI[ly * SP + lx] = v - c0;
     }
     __syncthreads();
     // vertical pass: SW columns x (TY / 4) row groups
@@ -261,6 +317,7 @@ __global__ void __launch_bounds__(256) k_fb_polyexp(const float* __restrict__ im
         }
         int y = y0 + ly;
         size_t plane = (size_t)w * h;
+        float out[5][4];
 #pragma unroll
         for (int o = 0; o < 4; o++) {
             float b1 = w0[o + N] * pc.g[0], b2 = 0.f, b3 = w1[o + N] * pc.g[0], b4 = 0.f, b5 = w2[o + N] * pc.g[0],
@@ -278,14 +335,26 @@ __global__ void __launch_bounds__(256) k_fb_polyexp(const float* __restrict__ im
                 b6 = fmaf(hi1 - lo1, pc.xg[k], b6);
                 b5 = fmaf(hi2 + lo2, pc.g[k], b5);
             }
-            int x = x0 + gx + o;
-            if (x < w && y < h) {
-                size_t at = (size_t)y * w + x;
-                store_r(R + at, b3 * pc.ig11);                                   // d/dy
-                store_r(R + plane + at, b2 * pc.ig11);                           // d/dx
-                store_r(R + 2 * plane + at, fmaf(b1, pc.ig03, b5 * pc.ig33));    // yy
-                store_r(R + 3 * plane + at, fmaf(b1, pc.ig03, b4 * pc.ig33));    // xx
-                store_r(R + 4 * plane + at, b6 * pc.ig55);                       // xy
+            out[0][o] = b3 * pc.ig11;                        // d/dy
+            out[1][o] = b2 * pc.ig11;                        // d/dx
+            out[2][o] = fmaf(b1, pc.ig03, b5 * pc.ig33);     // yy
+            out[3][o] = fmaf(b1, pc.ig03, b4 * pc.ig33);     // xx
+            out[4][o] = b6 * pc.ig55;                        // xy
+        }
+        int x = x0 + gx;
+        if (y < h) {
+            size_t at = (size_t)y * w + x;
+            if (sizeof(RT) == 4 && x + 4 <= w && (w & 3) == 0) {
+#pragma unroll
+                for (int c = 0; c < 5; c++)
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(R) + c * plane + at) =
+                        make_float4(out[c][0], out[c][1], out[c][2], out[c][3]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 5; c++)
+#pragma unroll
+                    for (int o = 0; o < 4; o++)
+                        if (x + o < w) store_r(R + c * plane + at + o, out[c][o]);
             }
         }
     }
@@ -475,12 +544,18 @@ extern "C" int tf_farneback_level_size(const tf_farneback* h, int li, int* width
 }
 
 template <typename RT>
-static int launch_polyexp(const tf_farneback* h, const FbLevel& L, int slot, cudaStream_t st) {
+static int launch_polyexp(const tf_farneback* h, const FbLevel& L, int slot, const uint8_t* gray_fused, cudaStream_t st) {
     dim3 grid(ceil_div(L.w, 64), ceil_div(L.h, 16));
     RT* R = reinterpret_cast<RT*>(L.R[slot]);
     ScopedKernelTimer timer(&L == &h->lv.back() ? TFK_FB_POLYEXP_FINEST : -1, st);
     switch (h->poly_n) {
-#define TF_PE(N) case N: k_fb_polyexp<N, RT><<<grid, 256, 0, st>>>(L.img, R, L.w, L.h, h->pc); break;
+#define TF_PE(N)                                                                                              \
+    case N:                                                                                               \
+        if (gray_fused)                                                                                   \
+            k_fb_polyexp<N, RT, true><<<grid, 256, 0, st>>>(nullptr, gray_fused, L.img, R, L.w, L.h, h->pc, 0.25f, 0.5f); \
+        else                                                                                              \
+            k_fb_polyexp<N, RT, false><<<grid, 256, 0, st>>>(L.img, nullptr, nullptr, R, L.w, L.h, h->pc, 0.f, 0.f);  \
+        break;
             TF_PE(1) TF_PE(2) TF_PE(3) TF_PE(4) TF_PE(5) TF_PE(6) TF_PE(7) TF_PE(8) TF_PE(9) TF_PE(10)
 #undef TF_PE
         default: return fail(TF_ERR_INVALID_ARG, "unsupported poly_n %d", h->poly_n);
@@ -494,11 +569,16 @@ extern "C" int tf_farneback_prepare(tf_farneback* h, int slot, const uint8_t* gr
     TF_REQUIRE(slot == 0 || slot == 1, TF_ERR_INVALID_ARG, "tf_farneback_prepare: slot must be 0 or 1");
     cudaStream_t st = as_stream(stream);
     for (auto& L : h->lv) {
-        k_fb_hpass<<<dim3(ceil_div(L.w, 256), h->H), 256, 0, st>>>(gray, h->T, L.gk, L.sx, L.tx, h->H, h->W, L.w, L.ksz);
-        TF_LAUNCHED();
-        k_fb_vpass<<<dim3(ceil_div(L.w, 256), L.h), 256, 0, st>>>(h->T, L.img, L.gk, L.sy, L.ty, h->H, L.w, L.h, L.ksz);
-        TF_LAUNCHED();
-        int e = h->r_fp16 ? launch_polyexp<__half>(h, L, slot, st) : launch_polyexp<float>(h, L, slot, st);
+        // the finest level (identity resize, sigma 0 -> fixed [1/4, 1/2, 1/4] taps) is fused into polyexp
+        bool fuse = L.w == h->W && L.h == h->H && L.ksz == 3 && L.sigma <= 0 && h->W >= 2 && h->H >= 2;
+        if (!fuse) {
+            k_fb_hpass<<<dim3(ceil_div(L.w, 256), h->H), 256, 0, st>>>(gray, h->T, L.gk, L.sx, L.tx, h->H, h->W, L.w, L.ksz);
+            TF_LAUNCHED();
+            k_fb_vpass<<<dim3(ceil_div(L.w, 256), L.h), 256, 0, st>>>(h->T, L.img, L.gk, L.sy, L.ty, h->H, L.w, L.h, L.ksz);
+            TF_LAUNCHED();
+        }
+        const uint8_t* g = fuse ? gray : nullptr;
+        int e = h->r_fp16 ? launch_polyexp<__half>(h, L, slot, g, st) : launch_polyexp<float>(h, L, slot, g, st);
         if (e) return e;
     }
     return TF_OK;

@@ -202,10 +202,13 @@ static int fb_launch_tile(const RT* R0, const RT* R1, const float2* in, float2* 
         TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
         attr_set = true;
     }
+    // CTAs are scheduled dynamically, so aim for ~4.5 waves of short CTAs: the tail costs about half a
+    // CTA instead of a partially filled wave; the price is the 2m-row vertical halo per chunk
     int per_sm = std::max(1, std::min(2, (int)((227 * 1024) / (G::SMEM + 1024))));
     int strips = ceil_div(w, FBT_TX);
-    int want = std::max(1, (per_sm * sm_count()) / strips);   // chunks that fill one wave
-    int rows = std::max(FBT_TY, ceil_div(ceil_div(h, want), FBT_TY) * FBT_TY);
+    int slots = per_sm * sm_count();
+    int rows = (int)((double)h * strips / (4.5 * slots) / FBT_TY + 0.5) * FBT_TY;
+    rows = std::max(2 * FBT_TY, std::min(rows, ceil_div(h, FBT_TY) * FBT_TY));
     dim3 grid(strips, ceil_div(h, rows));
     kern<<<grid, FBT_NT, G::SMEM, st>>>(R0, R1, in, dst, w, h, scale, rows, clip);
     return TF_OK;
