@@ -248,6 +248,7 @@ def test_horn_schunck_matches_reference(cfg):
     h, w = 270, 480
     g0, g1 = clip_pair(h, w, seed=4)
     hs = ops.HornSchunck(h, w)
+    hs.track_sweeps = True
     prev = None
     for rep in range(2):
         sweeps = []
@@ -271,6 +272,7 @@ def test_horn_schunck_early_exit_decision():
         sweeps = []
         want = F.horn_schunck(g0, g1, None, 1, 8, 0, delta, sweeps_out=sweeps)
         hs = ops.HornSchunck(h, w)
+        hs.track_sweeps = True
         got = hs(dev(g0), dev(g1), None, alpha=1, max_iters=8, decay=0, delta=delta).cpu().numpy()
         assert hs.last_sweeps == sweeps[0], (delta, hs.last_sweeps, sweeps[0])
         assert epe(got, want)[1] <= 0.1

@@ -18,10 +18,12 @@ struct tf_horn_schunck {
     float2* uv[2];
     float* rowsq;   // [H]  sum over x of d^2
     float* colsq;   // [W]
-    float* stats;   // [4] frobenius^2, max rowsq, max colsq, scratch
+    float* rowabs;  // [H]  sum over x of |d|
+    float* colabs;  // [W]
+    float* stats;   // [4] frobenius^2
     float* vx;      // [W] power-iteration vector
     float* vy;      // [H]
-    float* stats_host;  // pinned
+    struct HsState* state;  // device
 };
 
 #define HS_TX 32
@@ -90,15 +92,29 @@ __global__ void __launch_bounds__(256) k_hs_init(const float2* __restrict__ prev
     uv[i] = f;
 }
 
-// One Jacobi sweep.  Block 32 x 8.  Accumulates the squared change of u per row / column / total.
+// Device-side state of one tf_hs_run: the whole call is asynchronous, no host round trip per sweep.
+struct HsState {
+    int done;       // the early-exit test fired: later sweeps are no-ops
+    int sweeps;     // sweeps executed
+    int cur;        // index of the buffer holding the current (u, v)
+    int ambiguous;  // the cheap bounds could not decide; the power iteration must
+};
+
+// One Jacobi sweep.  Block 32 x 8.  Accumulates, for D = u_new - u_old: row / column sums of D^2 and
+// of |D| and the total of D^2 (bounds on the spectral norm, see k_hs_decide).
 __global__ void __launch_bounds__(256) k_hs_sweep(const float* __restrict__ Ex, const float* __restrict__ Ey,
-                                                  const float* __restrict__ Et, const float2* __restrict__ in,
-                                                  float2* __restrict__ out, float alpha2, int H, int W, int clip,
+                                                  const float* __restrict__ Et, float2* __restrict__ uv0,
+                                                  float2* __restrict__ uv1, float alpha2, int H, int W,
+                                                  const HsState* __restrict__ state, int track,
                                                   float* __restrict__ rowsq, float* __restrict__ colsq,
+                                                  float* __restrict__ rowabs, float* __restrict__ colabs,
                                                   float* __restrict__ stats) {
-    __shared__ float scol[8][32];
+    __shared__ float scol[2][8][32];
+    if (state->done) return;
+    const float2* in = state->cur ? uv1 : uv0;
+    float2* out = state->cur ? uv0 : uv1;
     int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    float d2 = 0.f;
+    float d2 = 0.f, da = 0.f;
     if (x < W && y < H) {
         int xm = max(x - 1, 0), xp = min(x + 1, W - 1), ym = max(y - 1, 0), yp = min(y + 1, H - 1);
         const float2* r0 = in + (size_t)ym * W;
@@ -114,98 +130,176 @@ __global__ void __launch_bounds__(256) k_hs_sweep(const float* __restrict__ Ex, 
         float un = ua - ex * c, vn = va - ey * c;
         float d = un - c11.x;
         d2 = d * d;
-        float2 o = make_float2(un, vn);
-        if (clip) {
-            o.x = fminf(fmaxf(o.x, (float)(-x)), (float)(W - 1 - x));
-            o.y = fminf(fmaxf(o.y, (float)(-y)), (float)(H - 1 - y));
-        }
-        out[at] = o;
+        da = fabsf(d);
+        out[at] = make_float2(un, vn);
     }
-    if (!rowsq) return;
-    // row partial: reduce over the 32 lanes of this warp (one warp == one row of the block)
-    float r = d2;
+    if (!track) return;
+    // row partials: one warp == one row of the block
+    float r = d2, ra = da;
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) r += __shfl_xor_sync(0xffffffffu, r, s);
+    for (int s = 16; s > 0; s >>= 1) {
+        r += __shfl_xor_sync(0xffffffffu, r, s);
+        ra += __shfl_xor_sync(0xffffffffu, ra, s);
+    }
     if (threadIdx.x == 0 && y < H) {
         atomicAdd(rowsq + y, r);
-        atomicAdd(stats, r);
+        atomicAdd(rowabs + y, ra);
     }
-    scol[threadIdx.y][threadIdx.x] = d2;
+    scol[0][threadIdx.y][threadIdx.x] = d2;
+    scol[1][threadIdx.y][threadIdx.x] = da;
     __syncthreads();
-    if (threadIdx.y == 0 && x < W) {
+    if (threadIdx.y < 2 && x < W) {
         float c = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; j++) c += scol[j][threadIdx.x];
-        atomicAdd(colsq + x, c);
+        for (int j = 0; j < 8; j++) c += scol[threadIdx.y][j][threadIdx.x];
+        atomicAdd((threadIdx.y ? colabs : colsq) + x, c);
     }
 }
 
-__global__ void __launch_bounds__(256) k_hs_max(const float* __restrict__ v, int n, float* __restrict__ out) {
-    __shared__ float s[256];
-    float m = 0.f;
-    for (int i = threadIdx.x; i < n; i += 256) m = fmaxf(m, v[i]);
-    s[threadIdx.x] = m;
+__device__ __forceinline__ float hs_block_max(float v, float* sh) {
+    int t = threadIdx.x;
+    sh[t] = v;
     __syncthreads();
-    for (int k = 128; k > 0; k >>= 1) {
-        if (threadIdx.x < k) s[threadIdx.x] = fmaxf(s[threadIdx.x], s[threadIdx.x + k]);
+    for (int k = blockDim.x >> 1; k > 0; k >>= 1) {
+        if (t < k) sh[t] = fmaxf(sh[t], sh[t + k]);
         __syncthreads();
     }
-    if (threadIdx.x == 0) *out = s[0];
+    float m = sh[0];
+    __syncthreads();
+    return m;
 }
 
-// Power iteration helpers on D = u_new - u_old (H x W): y = D x ; x = D^T y.
-__global__ void __launch_bounds__(256) k_hs_dx(const float2* __restrict__ un, const float2* __restrict__ uo,
-                                               const float* __restrict__ vx, float* __restrict__ vy, int H, int W) {
-    int y = blockIdx.x;
-    __shared__ float s[256];
-    float acc = 0.f;
-    for (int x = threadIdx.x; x < W; x += 256) {
-        size_t at = (size_t)y * W + x;
-        acc += (un[at].x - uo[at].x) * vx[x];
-    }
-    s[threadIdx.x] = acc;
+__device__ __forceinline__ float hs_block_sum(float v, float* sh) {
+    int t = threadIdx.x;
+    sh[t] = v;
     __syncthreads();
-    for (int k = 128; k > 0; k >>= 1) {
-        if (threadIdx.x < k) s[threadIdx.x] += s[threadIdx.x + k];
+    for (int k = blockDim.x >> 1; k > 0; k >>= 1) {
+        if (t < k) sh[t] += sh[t + k];
         __syncthreads();
     }
-    if (threadIdx.x == 0) vy[y] = s[0];
-}
-
-__global__ void __launch_bounds__(256) k_hs_dty(const float2* __restrict__ un, const float2* __restrict__ uo,
-                                                const float* __restrict__ vy, float* __restrict__ vx, int H, int W) {
-    int x = blockIdx.x * 256 + threadIdx.x;
-    if (x >= W) return;
-    float acc = 0.f;
-    for (int y = 0; y < H; y++) {
-        size_t at = (size_t)y * W + x;
-        acc += (un[at].x - uo[at].x) * vy[y];
-    }
-    vx[x] = acc;
-}
-
-// x <- x / ||x||; writes ||x|| to *norm_out
-__global__ void __launch_bounds__(256) k_hs_normalize(float* __restrict__ v, int n, float* __restrict__ norm_out) {
-    __shared__ float s[256];
-    float acc = 0.f;
-    for (int i = threadIdx.x; i < n; i += 256) acc += v[i] * v[i];
-    s[threadIdx.x] = acc;
+    float m = sh[0];
     __syncthreads();
-    for (int k = 128; k > 0; k >>= 1) {
-        if (threadIdx.x < k) s[threadIdx.x] += s[threadIdx.x + k];
+    return m;
+}
+
+// After a sweep: book-keeping plus the early-exit test of horn_schunck.py:43 on the device.
+//   max(row 2-norm, column 2-norm) <= sigma_max(D) <= min(||D||_F, sqrt(||D||_1 * ||D||_inf))
+// delta above the upper bound -> converged; at or below the lower bound -> keep sweeping; in between
+// the power iteration (k_hs_power) decides.  Also clears the accumulators for the next sweep.
+__global__ void __launch_bounds__(256) k_hs_decide(HsState* state, float* rowsq, float* colsq, float* rowabs,
+                                                   float* colabs, float* stats, int H, int W, float delta, int check) {
+    __shared__ float sh[256];
+    if (state->done) return;
+    float mr = 0.f, mc = 0.f, ar = 0.f, ac = 0.f, frob2 = 0.f;
+    if (check) {
+        for (int i = threadIdx.x; i < H; i += 256) {
+            mr = fmaxf(mr, rowsq[i]);
+            ar = fmaxf(ar, rowabs[i]);
+            frob2 += rowsq[i];   // ||D||_F^2 = sum of the row sums (no single-address atomic in the sweep)
+        }
+        for (int i = threadIdx.x; i < W; i += 256) {
+            mc = fmaxf(mc, colsq[i]);
+            ac = fmaxf(ac, colabs[i]);
+        }
+        mr = hs_block_max(mr, sh);
+        mc = hs_block_max(mc, sh);
+        ar = hs_block_max(ar, sh);   // ||D||_inf (max absolute row sum)
+        ac = hs_block_max(ac, sh);   // ||D||_1   (max absolute column sum)
+        frob2 = hs_block_sum(frob2, sh);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H; i += 256) rowsq[i] = rowabs[i] = 0.f;
+    for (int i = threadIdx.x; i < W; i += 256) colsq[i] = colabs[i] = 0.f;
+    if (threadIdx.x == 0) {
+        stats[0] = 0.f;
+        state->sweeps += 1;
+        state->cur ^= 1;
+        if (check) {
+            float upper = fminf(sqrtf(frob2), sqrtf(ar * ac));
+            float lower = sqrtf(fmaxf(mr, mc));
+            if (upper < delta) state->done = 1;
+            else if (lower < delta) state->ambiguous = 1;
+        }
+    }
+}
+
+// Rare path: power iteration on D^T D, one block (the decision is needed on the device, in stream
+// order, and the common case must cost one empty launch).  ||D x|| with ||x|| = 1 is a lower bound of
+// sigma_max that grows monotonically; reaching delta means "keep sweeping".
+__global__ void __launch_bounds__(1024) k_hs_power(HsState* state, const float2* __restrict__ uv0,
+                                                   const float2* __restrict__ uv1, float* vx, float* vy, int H, int W,
+                                                   float delta, int max_steps) {
+    __shared__ float sh[1024];
+    if (state->done || !state->ambiguous) return;
+    const float2* un = state->cur ? uv1 : uv0;  // k_hs_decide already flipped cur: un = newest
+    const float2* uo = state->cur ? uv0 : uv1;
+    int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < W; i += 1024) vx[i] = rsqrtf((float)W);
+    __syncthreads();
+    bool reaches = false;
+    for (int step = 0; step < max_steps && !reaches; step++) {
+        // vy = D vx (one warp per row)
+        for (int y = warp; y < H; y += 32) {
+            float acc = 0.f;
+            for (int x = lane; x < W; x += 32) {
+                size_t at = (size_t)y * W + x;
+                acc += (un[at].x - uo[at].x) * vx[x];
+            }
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+            if (lane == 0) vy[y] = acc;
+        }
+        __syncthreads();
+        float part = 0.f;
+        for (int i = t; i < H; i += 1024) part += vy[i] * vy[i];
+        float ny = sqrtf(hs_block_sum(part, sh));
+        if (ny >= delta) {
+            reaches = true;
+            break;
+        }
+        if (ny == 0.f) break;
+        // vx = D^T vy / ||.||  (one thread per column, rows strided: coalesced across threads)
+        for (int x = t; x < W; x += 1024) {
+            float acc = 0.f;
+            for (int y = 0; y < H; y++) {
+                size_t at = (size_t)y * W + x;
+                acc += (un[at].x - uo[at].x) * vy[y];
+            }
+            vx[x] = acc;
+        }
+        __syncthreads();
+        part = 0.f;
+        for (int i = t; i < W; i += 1024) part += vx[i] * vx[i];
+        float nx = sqrtf(hs_block_sum(part, sh));
+        if (nx == 0.f) break;
+        float inv = 1.f / nx;
+        for (int i = t; i < W; i += 1024) vx[i] *= inv;
         __syncthreads();
     }
-    float nrm = sqrtf(s[0]);
-    if (threadIdx.x == 0) *norm_out = nrm;
-    float inv = nrm > 0.f ? 1.f / nrm : 0.f;
-    for (int i = threadIdx.x; i < n; i += 256) v[i] *= inv;
+    if (t == 0) {
+        state->ambiguous = 0;
+        if (!reaches) state->done = 1;
+    }
 }
 
-// copy-out with the final clip of FlowSource.post_process (source.py:361-362) fused in
-__global__ void __launch_bounds__(256) k_hs_copy_out(const float2* __restrict__ src, float2* __restrict__ dst, int H,
-                                                     int W, int clip) {
+__global__ void k_hs_begin(HsState* state, float* rowsq, float* colsq, float* rowabs, float* colabs, float* stats,
+                           int H, int W) {
+    for (int i = threadIdx.x; i < H; i += blockDim.x) rowsq[i] = rowabs[i] = 0.f;
+    for (int i = threadIdx.x; i < W; i += blockDim.x) colsq[i] = colabs[i] = 0.f;
+    if (threadIdx.x == 0) {
+        stats[0] = 0.f;
+        state->done = state->sweeps = state->cur = state->ambiguous = 0;
+    }
+}
+
+// copy-out of the buffer the state points at, with the final clip of FlowSource.post_process
+// (source.py:361-362) fused in
+__global__ void __launch_bounds__(256) k_hs_copy_out(const float2* __restrict__ uv0, const float2* __restrict__ uv1,
+                                                     const HsState* __restrict__ state, float2* __restrict__ dst,
+                                                     int H, int W, int clip) {
     int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
+    const float2* src = state->cur ? uv1 : uv0;
     float2 o = src[(size_t)y * W + x];
     if (clip) {
         o.x = fminf(fmaxf(o.x, (float)(-x)), (float)(W - 1 - x));
@@ -214,16 +308,11 @@ __global__ void __launch_bounds__(256) k_hs_copy_out(const float2* __restrict__ 
     dst[(size_t)y * W + x] = o;
 }
 
-__global__ void __launch_bounds__(256) k_hs_fill(float* v, int n, float val) {
-    int i = blockIdx.x * 256 + threadIdx.x;
-    if (i < n) v[i] = val;
-}
-
 extern "C" int tf_hs_destroy(tf_horn_schunck* h) {
     if (!h) return TF_OK;
     cudaFree(h->Ex); cudaFree(h->Ey); cudaFree(h->Et); cudaFree(h->uv[0]); cudaFree(h->uv[1]);
-    cudaFree(h->rowsq); cudaFree(h->colsq); cudaFree(h->stats); cudaFree(h->vx); cudaFree(h->vy);
-    if (h->stats_host) cudaFreeHost(h->stats_host);
+    cudaFree(h->rowsq); cudaFree(h->colsq); cudaFree(h->rowabs); cudaFree(h->colabs); cudaFree(h->stats);
+    cudaFree(h->vx); cudaFree(h->vy); cudaFree(h->state);
     delete h;
     return TF_OK;
 }
@@ -242,41 +331,15 @@ extern "C" int tf_hs_create(tf_horn_schunck** out, int height, int width) {
     bool ok = cudaMalloc(&h->Ex, n * 4) == cudaSuccess && cudaMalloc(&h->Ey, n * 4) == cudaSuccess &&
               cudaMalloc(&h->Et, n * 4) == cudaSuccess && cudaMalloc(&h->uv[0], n * 8) == cudaSuccess &&
               cudaMalloc(&h->uv[1], n * 8) == cudaSuccess && cudaMalloc(&h->rowsq, height * 4) == cudaSuccess &&
-              cudaMalloc(&h->colsq, width * 4) == cudaSuccess && cudaMalloc(&h->stats, 16) == cudaSuccess &&
+              cudaMalloc(&h->colsq, width * 4) == cudaSuccess && cudaMalloc(&h->rowabs, height * 4) == cudaSuccess &&
+              cudaMalloc(&h->colabs, width * 4) == cudaSuccess && cudaMalloc(&h->stats, 16) == cudaSuccess &&
               cudaMalloc(&h->vx, width * 4) == cudaSuccess && cudaMalloc(&h->vy, height * 4) == cudaSuccess &&
-              cudaMallocHost(&h->stats_host, 16) == cudaSuccess;
+              cudaMalloc(&h->state, sizeof(HsState)) == cudaSuccess;
     if (!ok) {
         tf_hs_destroy(h);
         return fail(TF_ERR_CUDA, "tf_hs_create: allocation failed for %dx%d", height, width);
     }
     *out = h;
-    return TF_OK;
-}
-
-// sigma_max(D) >= delta ?  Power iteration on D^T D gives a monotone lower bound.
-static int hs_sigma_reaches(tf_horn_schunck* h, const float2* un, const float2* uo, double delta, bool* reaches,
-                            cudaStream_t st) {
-    k_hs_fill<<<ceil_div(h->W, 256), 256, 0, st>>>(h->vx, h->W, 1.0f / sqrtf((float)h->W));
-    TF_LAUNCHED();
-    *reaches = false;
-    for (int it = 0; it < 64; it++) {
-        k_hs_dx<<<h->H, 256, 0, st>>>(un, uo, h->vx, h->vy, h->H, h->W);
-        TF_LAUNCHED();
-        k_hs_normalize<<<1, 256, 0, st>>>(h->vy, h->H, h->stats + 3);  // ||D x|| with ||x|| = 1: a lower bound
-        TF_LAUNCHED();
-        k_hs_dty<<<ceil_div(h->W, 256), 256, 0, st>>>(un, uo, h->vy, h->vx, h->H, h->W);
-        TF_LAUNCHED();
-        k_hs_normalize<<<1, 256, 0, st>>>(h->vx, h->W, h->stats + 2);
-        TF_LAUNCHED();
-        if ((it & 7) == 7) {
-            TF_CUDA(cudaMemcpyAsync(h->stats_host, h->stats, 16, cudaMemcpyDeviceToHost, st));
-            TF_CUDA(cudaStreamSynchronize(st));
-            if ((double)h->stats_host[3] >= delta) {
-                *reaches = true;
-                return TF_OK;
-            }
-        }
-    }
     return TF_OK;
 }
 
@@ -293,49 +356,39 @@ extern "C" int tf_hs_run(tf_horn_schunck* h, const uint8_t* left, const uint8_t*
     k_hs_derivatives<<<dim3(ceil_div(W, HS_TX), ceil_div(H, HS_TY)), dim3(HS_TX, HS_TY), 0, st>>>(left, right, h->Ex,
                                                                                                  h->Ey, h->Et, H, W);
     TF_LAUNCHED();
-    float2* out = reinterpret_cast<float2*>(flow);
-    // ping-pong so that the last sweep that runs writes `out`... the number of sweeps is only known
-    // at run time (early exit), so sweeps alternate between two scratch planes and the result is
-    // copied (or clipped) into `out` at the end.
     k_hs_init<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(prev_flow), h->uv[0],
                                                           (float)decay, n);
     TF_LAUNCHED();
-    int cur = 0, done = 0;
+    k_hs_begin<<<1, 256, 0, st>>>(h->state, h->rowsq, h->colsq, h->rowabs, h->colabs, h->stats, H, W);
+    TF_LAUNCHED();
+    // The sweep count is only known on the device (early exit): every launch below is conditional on
+    // the device-side state, nothing here waits for the GPU.
     bool track = delta >= 0;
     dim3 grid(ceil_div(W, 32), ceil_div(H, 8)), block(32, 8);
     for (int it = 0; it < max_iters; it++) {
-        if (track) {
-            TF_CUDA(cudaMemsetAsync(h->rowsq, 0, H * 4, st));
-            TF_CUDA(cudaMemsetAsync(h->colsq, 0, W * 4, st));
-            TF_CUDA(cudaMemsetAsync(h->stats, 0, 16, st));
-        }
+        bool check = track && it + 1 < max_iters;  // the reference's test after the last sweep changes nothing
         {
             ScopedKernelTimer timer(TFK_HS_SWEEP, st);
-            k_hs_sweep<<<grid, block, 0, st>>>(h->Ex, h->Ey, h->Et, h->uv[cur], h->uv[cur ^ 1], (float)(alpha * alpha), H,
-                                               W, 0, track ? h->rowsq : nullptr, h->colsq, h->stats);
+            k_hs_sweep<<<grid, block, 0, st>>>(h->Ex, h->Ey, h->Et, h->uv[0], h->uv[1], (float)(alpha * alpha), H, W,
+                                               h->state, check, h->rowsq, h->colsq, h->rowabs, h->colabs, h->stats);
         }
         TF_LAUNCHED();
-        cur ^= 1;
-        done++;
-        if (track && it + 1 < max_iters) {
-            k_hs_max<<<1, 256, 0, st>>>(h->rowsq, H, h->stats + 1);
+        k_hs_decide<<<1, 256, 0, st>>>(h->state, h->rowsq, h->colsq, h->rowabs, h->colabs, h->stats, H, W, (float)delta,
+                                       check);
+        TF_LAUNCHED();
+        if (check) {
+            k_hs_power<<<1, 1024, 0, st>>>(h->state, h->uv[0], h->uv[1], h->vx, h->vy, H, W, (float)delta, 48);
             TF_LAUNCHED();
-            k_hs_max<<<1, 256, 0, st>>>(h->colsq, W, h->stats + 2);
-            TF_LAUNCHED();
-            TF_CUDA(cudaMemcpyAsync(h->stats_host, h->stats, 16, cudaMemcpyDeviceToHost, st));
-            TF_CUDA(cudaStreamSynchronize(st));
-            double upper = sqrt((double)h->stats_host[0]);
-            double lower = sqrt((double)fmaxf(h->stats_host[1], h->stats_host[2]));
-            if (upper < delta) break;  // sigma_max <= ||D||_F < delta: converged
-            if (lower < delta) {       // undecided: ask the power iteration
-                bool reaches = false;
-                if (int e = hs_sigma_reaches(h, h->uv[cur], h->uv[cur ^ 1], delta, &reaches, st)) return e;
-                if (!reaches) break;
-            }
         }
     }
-    k_hs_copy_out<<<dim3(ceil_div(W, 256), H), 256, 0, st>>>(h->uv[cur], out, H, W, clip);
+    k_hs_copy_out<<<dim3(ceil_div(W, 256), H), 256, 0, st>>>(h->uv[0], h->uv[1], h->state, reinterpret_cast<float2*>(flow),
+                                                             H, W, clip);
     TF_LAUNCHED();
-    if (sweeps_done_host) *sweeps_done_host = done;
+    if (sweeps_done_host) {  // only tests ask: this is the one place that waits for the device
+        HsState hs;
+        TF_CUDA(cudaMemcpyAsync(&hs, h->state, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        TF_CUDA(cudaStreamSynchronize(st));
+        *sweeps_done_host = hs.sweeps;
+    }
     return TF_OK;
 }

@@ -109,7 +109,8 @@ class HornSchunck:
         self.h, self.w = int(height), int(width)
         self.handle = C.c_void_p()
         check(self.lib.tf_hs_create(C.byref(self.handle), self.h, self.w))
-        self.last_sweeps = 0
+        self.last_sweeps = None
+        self.track_sweeps = False
 
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:
@@ -128,10 +129,11 @@ class HornSchunck:
         if out is None:
             out = torch.empty((self.h, self.w, 2), dtype=torch.float32, device="cuda")
         sweeps = C.c_int(0)
+        # asking for the sweep count makes the call wait for the device; off by default
         check(self.lib.tf_hs_run(self.handle, ptr(left), ptr(right), ptr(flow), float(alpha), int(max_iters),
                                  float(decay), -1.0 if delta is None else float(delta), ptr(out),
-                                 int(bool(clip)), C.byref(sweeps), stream_ptr()))
-        self.last_sweeps = sweeps.value
+                                 int(bool(clip)), C.byref(sweeps) if self.track_sweeps else None, stream_ptr()))
+        self.last_sweeps = sweeps.value if self.track_sweeps else None
         return out
 
 
