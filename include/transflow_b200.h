@@ -122,6 +122,12 @@ TF_API int tf_lk_run(tf_lucas_kanade* h, const uint8_t* left, const uint8_t* rig
 TF_API int tf_flow_postprocess(float* flow, const float* mask, int forward, int32_t* owner, int height,
                         int width, void* stream);
 
+/* Same, writing the post-processed flow to `out` instead of in place (out may be PEER memory: the
+ * last kernel of the producer stores straight into the accumulator rank's ring slot over NVLink).
+ * out == NULL or out == flow -> in place. */
+TF_API int tf_flow_postprocess_to(float* flow, const float* mask, int forward, int32_t* owner, float* out,
+                                  int height, int width, void* stream);
+
 /* ---- compositor: transflow/compositor/** ---------------------------------------------------- */
 enum { TF_LAYER_MOVEREF = 0, TF_LAYER_SUM = 1, TF_LAYER_STATIC = 2, TF_LAYER_INTRODUCTION = 3 };
 enum { TF_RESET_OFF = 0, TF_RESET_RANDOM = 1, TF_RESET_CONSTANT = 2, TF_RESET_LINEAR = 3 };
@@ -194,6 +200,10 @@ TF_API int tf_layer_set_counters(tf_layer* l, uint64_t frames, int introduced_on
 /* ---- multi-GPU flow hand-off over NVLink (frame pairs sharded across ranks) ---------------- */
 /* CUDA IPC plumbing so a producer rank's last flow kernel stores straight into the
  * accumulator rank's ring slot (peer memory), followed by a release flag. */
+/* Raw device allocations (cudaMalloc, 256-byte aligned) for buffers that are shared through CUDA IPC:
+ * a framework caching allocator hands out interior pointers, IPC handles name whole allocations. */
+TF_API int tf_device_malloc(size_t bytes, void** dev_ptr_out);
+TF_API int tf_device_free(void* dev_ptr);
 TF_API int tf_ipc_get_handle(const void* dev_ptr, uint8_t handle_out_host[64]);
 TF_API int tf_ipc_open_handle(const uint8_t handle_host[64], void** dev_ptr_out);
 TF_API int tf_ipc_close_handle(void* dev_ptr);

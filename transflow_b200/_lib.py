@@ -80,6 +80,9 @@ SIGNATURES = {
     "tf_lk_destroy": (_i, [_vp]),
     "tf_lk_run": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "tf_flow_postprocess": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp]),
+    "tf_flow_postprocess_to": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "tf_device_malloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
+    "tf_device_free": (_i, [_vp]),
     "tf_layer_create": (_i, [C.POINTER(_vp), _i, _i, C.POINTER(LayerConfigStruct)]),
     "tf_layer_destroy": (_i, [_vp]),
     "tf_layer_set_masks": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
@@ -147,6 +150,8 @@ def ptr(t):
     """Device pointer of a torch tensor (None -> NULL)."""
     if t is None:
         return C.c_void_p(0)
+    if isinstance(t, int):          # a raw device address (e.g. a CUDA-IPC mapping of peer memory)
+        return C.c_void_p(t)
     return C.c_void_p(t.data_ptr())
 
 

@@ -154,8 +154,8 @@ __device__ __forceinline__ float2 clip_flow(float2 f, int x, int y, int w, int h
 }
 
 // backward direction: optional mask multiply + final clip.
-__global__ void __launch_bounds__(256) k_post_backward(float2* __restrict__ flow, const float* __restrict__ mask,
-                                                       int h, int w) {
+__global__ void __launch_bounds__(256) k_post_backward(const float2* __restrict__ flow, const float* __restrict__ mask,
+                                                       float2* __restrict__ out, int h, int w) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;
     if (x >= w) return;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256) k_post_backward(float2* __restrict__ flow
         f.x = __fmul_rn(m, f.x);
         f.y = __fmul_rn(m, f.y);
     }
-    flow[p] = clip_flow(f, x, y, w, h);
+    out[p] = clip_flow(f, x, y, w, h);
 }
 
 // forward pass 1: clip, round half-even, claim the target with atomicMax(source index + 1):
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256) k_post_forward_scatter(const float2* __re
 }
 
 // forward pass 2: flow := owner position - own position (0 where unclaimed); owner plane re-zeroed.
-__global__ void __launch_bounds__(256) k_post_forward_gather(float2* __restrict__ flow, int* __restrict__ owner,
+__global__ void __launch_bounds__(256) k_post_forward_gather(float2* __restrict__ out, int* __restrict__ owner,
                                                              int h, int w) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;
@@ -208,26 +208,33 @@ __global__ void __launch_bounds__(256) k_post_forward_gather(float2* __restrict_
         f.x = (float)(s % w - x);
         f.y = (float)(s / w - y);
     }
-    flow[p] = f;  // already inside the frame: the final clip is the identity here
+    out[p] = f;  // already inside the frame: the final clip is the identity here
 }
 
-extern "C" int tf_flow_postprocess(float* flow, const float* mask, int forward, int32_t* owner, int height, int width,
-                                   void* stream) {
+extern "C" int tf_flow_postprocess_to(float* flow, const float* mask, int forward, int32_t* owner, float* out,
+                                      int height, int width, void* stream) {
     TF_REQUIRE(flow, TF_ERR_INVALID_ARG, "tf_flow_postprocess: null flow");
     TF_REQUIRE(height > 0 && width > 0, TF_ERR_SHAPE, "tf_flow_postprocess: bad shape %dx%d", height, width);
     TF_REQUIRE(!forward || owner, TF_ERR_INVALID_ARG, "tf_flow_postprocess: forward direction needs the owner plane");
     if (int e = require_sm100()) return e;
+    if (!out) out = flow;
     dim3 grid(ceil_div(width, 256), height);
     cudaStream_t st = as_stream(stream);
     if (!forward) {
-        k_post_backward<<<grid, 256, 0, st>>>(reinterpret_cast<float2*>(flow), mask, height, width);
+        k_post_backward<<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(flow), mask, reinterpret_cast<float2*>(out),
+                                              height, width);
         TF_LAUNCHED();
     } else {
         ScopedKernelTimer timer(TFK_POST_FORWARD, st);
         k_post_forward_scatter<<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(flow), mask, owner, height, width);
         TF_LAUNCHED();
-        k_post_forward_gather<<<grid, 256, 0, st>>>(reinterpret_cast<float2*>(flow), owner, height, width);
+        k_post_forward_gather<<<grid, 256, 0, st>>>(reinterpret_cast<float2*>(out), owner, height, width);
         TF_LAUNCHED();
     }
     return TF_OK;
+}
+
+extern "C" int tf_flow_postprocess(float* flow, const float* mask, int forward, int32_t* owner, int height, int width,
+                                   void* stream) {
+    return tf_flow_postprocess_to(flow, mask, forward, owner, nullptr, height, width, stream);
 }

@@ -8,6 +8,18 @@
 
 using namespace tf;
 
+extern "C" int tf_device_malloc(size_t bytes, void** dev_ptr_out) {
+    TF_REQUIRE(dev_ptr_out && bytes > 0, TF_ERR_INVALID_ARG, "tf_device_malloc: bad argument");
+    TF_CUDA(cudaMalloc(dev_ptr_out, bytes));
+    TF_CUDA(cudaMemset(*dev_ptr_out, 0, bytes));
+    return TF_OK;
+}
+
+extern "C" int tf_device_free(void* dev_ptr) {
+    if (dev_ptr) TF_CUDA(cudaFree(dev_ptr));
+    return TF_OK;
+}
+
 extern "C" int tf_ipc_get_handle(const void* dev_ptr, uint8_t handle_out[64]) {
     TF_REQUIRE(dev_ptr && handle_out, TF_ERR_INVALID_ARG, "tf_ipc_get_handle: null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "unexpected IPC handle size");

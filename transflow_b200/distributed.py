@@ -16,6 +16,8 @@ a round together with the producers when ``c0 = q * (1 - (N - 1) * A/F) / (1 + A
 Rank 0 posts the receives of round j + 1 before it consumes round j (two buffer sets), so
 producers run one round ahead of the accumulator instead of stalling on it.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -54,8 +56,9 @@ class ShardedFlowStream:
     """
 
     def __init__(self, rank, world, chunk_pairs, counts, estimate_chunk, accumulate, flow_shape, device,
-                 group=None):
+                 group=None, transport="nccl"):
         self.rank, self.world, self.k = rank, world, chunk_pairs
+        self.transport = transport
         self.counts = list(counts)
         self.owners = round_slots(self.counts)
         self.cpr = len(self.owners)
@@ -63,6 +66,13 @@ class ShardedFlowStream:
         self.flow_shape, self.device, self.group = tuple(flow_shape), device, group
         self.frames_accumulated = 0
         self._recv = {}      # (round parity, slot) -> K receive buffers
+        self.ring = None
+        if transport == "p2p" and world > 1:
+            from .peer import PeerFlowRing
+            flows_per_round = [c * chunk_pairs for c in self.counts]
+            self.ring = PeerFlowRing(rank, world, flows_per_round, self.flow_shape, group)
+            self._published = 0                       # producer: flows published so far
+            self._expected = [0] * world              # rank 0: flows consumed so far per producer
 
     @property
     def frames_per_round(self) -> int:
@@ -85,10 +95,43 @@ class ShardedFlowStream:
                 pending[slot] = dist.batch_isend_irecv(ops)
         return pending
 
+    def _run_p2p(self, first_round: int, n_rounds: int):
+        """Same schedule; flows land in rank 0's ring by peer stores, counters replace send/recv."""
+        ring = self.ring
+        for j in range(first_round, first_round + n_rounds):
+            base_chunk = j * self.cpr
+            if self.rank == 0:
+                index = [0] * self.world              # next ring slot per producer in this round
+                for slot, owner in enumerate(self.owners):
+                    if owner == 0:
+                        flows = self.estimate_chunk((base_chunk + slot) * self.k, self.k)
+                    else:
+                        self._expected[owner] += self.k
+                        ring.wait_ready(owner, self._expected[owner])
+                        flows = [ring.slot_tensor(owner, j, index[owner] + i) for i in range(self.k)]
+                        index[owner] += self.k
+                    for f in flows:
+                        self.accumulate(f)
+                        self.frames_accumulated += 1
+                    if owner != 0 and index[owner] == self.counts[owner] * self.k:
+                        ring.release(owner, j)        # every flow of this producer's round is consumed
+            else:
+                ring.wait_slot_free(j)
+                i = 0
+                for slot, owner in enumerate(self.owners):
+                    if owner == self.rank:
+                        outs = [ring.slot_address(j, i + n) for n in range(self.k)]
+                        self.estimate_chunk((base_chunk + slot) * self.k, self.k, outs)
+                        i += self.k
+                        self._published += self.k
+                        ring.publish(self._published)
+
     def run(self, first_round: int, n_rounds: int):
         """Process rounds [first_round, first_round + n_rounds)."""
         if n_rounds <= 0:
             return
+        if self.ring is not None:
+            return self._run_p2p(first_round, n_rounds)
         last = first_round + n_rounds - 1
         if self.rank == 0:
             pending = self._post_receives(first_round)
@@ -171,7 +214,7 @@ def bench_sharded(args, rank, world, local):
     import bench as B
 
     H, W = args.height, args.width
-    K, Q = 4, 4
+    K, Q = 8, 4
     clip, mask, pixmap = B.build_workload(H, W, B.N_DISTINCT, seed=0)
     frames_dev = torch.from_numpy(clip).cuda()
     feeder = _HostFrameFeeder(torch.from_numpy(clip).pin_memory(), lambda i: B.frame_order(i, B.N_DISTINCT))
@@ -183,8 +226,9 @@ def bench_sharded(args, rank, world, local):
     post = ops.PostProcess(H, W, forward=True)
     gray = torch.empty((H, W), dtype=torch.uint8, device="cuda")
 
-    def estimate_chunk(first_pair, n_pairs):
-        """K consecutive pairs: K + 1 prepares (one extra per chunk), K solves + post-processes."""
+    def estimate_chunk(first_pair, n_pairs, outs=None):
+        """K consecutive pairs: K + 1 prepares (one extra per chunk), K solves + post-processes.
+        ``outs`` (raw device addresses, possibly peer memory) receive the post-processed flows."""
         slot = 0
         ops.gray_from_bgr(frame(first_pair), gray)
         fb.prepare(slot, gray)
@@ -194,7 +238,7 @@ def bench_sharded(args, rank, world, local):
             ops.gray_from_bgr(frame(first_pair + i + 1), gray)
             fb.prepare(cur, gray)
             flow = fb.solve(slot, cur)          # forward: (prev, cur)
-            flows.append(post(flow))
+            flows.append(post(flow, None if outs is None else outs[i]))
             slot = cur
         return flows
 
@@ -248,7 +292,9 @@ def bench_sharded(args, rank, world, local):
     dist.broadcast(plan, src=0)
     f_ms, a_ms = float(plan[0]), float(plan[1])
     counts = plan_round(world, Q, f_ms, a_ms)
-    stream = ShardedFlowStream(rank, world, K, counts, estimate_chunk, accumulate, (H, W, 2), "cuda")
+    transport = os.environ.get("TFB200_TRANSPORT", "p2p")
+    stream = ShardedFlowStream(rank, world, K, counts, estimate_chunk, accumulate, (H, W, 2), "cuda",
+                               transport=transport)
 
     def timed_rounds(first):
         stream.run(first, args.warmup)
@@ -265,19 +311,21 @@ def bench_sharded(args, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t
 
-    # end to end first: every frame enters from pinned host memory, every RGB frame returns to it
-    io["host"] = True
-    ms_e2e = timed_rounds(0)
-    io["host"] = False
     sampler = B.ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
-    ms = timed_rounds(args.warmup + args.steps)
-    launches = torch.tensor([_lib.launch_count() - launches0], dtype=torch.float64, device="cuda")
+    ms = timed_rounds(0)
+    launches_done = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    # end to end: every frame enters from pinned host memory, every RGB frame returns to it
+    io["host"] = True
+    ms_e2e = timed_rounds(args.warmup + args.steps)
+    io["host"] = False
+    launches = torch.tensor([launches_done], dtype=torch.float64, device="cuda")
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
     if rank == 0:
-        clocks = sampler.stop()
+        checksum = int(torch.from_numpy(comp.layers[0].data).long().sum())   # same for every transport
         frames = args.steps * stream.frames_per_round
         fps = frames / (float(ms) / 1000.0)
         peak, peak_src = B.measured_peak_gbs()
@@ -288,8 +336,11 @@ def bench_sharded(args, rank, world, local):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms) / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(B.workload_config(args), sharding=f"chunks of {K} pairs; per round {counts} chunks per rank "
-                           f"(rank 0 also runs the sequential accumulate+remap); flows sent to rank 0 with batched "
-                           f"NCCL send/recv, receives posted one round ahead", frames_per_step=stream.frames_per_round,
+                           f"(rank 0 also runs the sequential accumulate+remap); transport {transport}: "
+                           + ("the producer's last post-process kernel stores the flow into rank 0's ring over NVLink "
+                              "peer memory, counters + cuStreamWaitValue32 order it" if transport == "p2p" else
+                              "batched NCCL send/recv, receives posted one round ahead"),
+                           frames_per_step=stream.frames_per_round, state_checksum=checksum,
                            calibrated_ms={"flow_per_pair": f_ms, "accumulate_per_frame": a_ms}),
             "roofline": None,
             "e2e": {"value": frames / (float(ms_e2e) / 1000.0), "unit": "frames/s",

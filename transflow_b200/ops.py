@@ -173,10 +173,11 @@ class PostProcess:
         self.mask = None if mask is None else _cuda(mask, torch.float32, "mask").reshape(self.h, self.w)
         self.owner = torch.zeros((self.h, self.w), dtype=torch.int32, device="cuda") if self.forward else None
 
-    def __call__(self, flow: torch.Tensor) -> torch.Tensor:
+    def __call__(self, flow: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """In place by default; ``out`` (same shape, may be peer memory) receives the result instead."""
         flow = _cuda(flow, torch.float32, "flow")
         if tuple(flow.shape) != (self.h, self.w, 2):
             raise ValueError(f"flow must be ({self.h}, {self.w}, 2), got {tuple(flow.shape)}")
-        check(self.lib.tf_flow_postprocess(ptr(flow), ptr(self.mask), int(self.forward), ptr(self.owner), self.h,
-                                           self.w, stream_ptr()))
-        return flow
+        check(self.lib.tf_flow_postprocess_to(ptr(flow), ptr(self.mask), int(self.forward), ptr(self.owner), ptr(out),
+                                              self.h, self.w, stream_ptr()))
+        return flow if out is None else out
