@@ -390,3 +390,69 @@ def test_farneback_other_window_sizes(params):
         got = ops.Farneback(h, w, variant=variant, **params)(dev(g0), dev(g1)).cpu().numpy()
         mean, mx = epe(got, want)
         assert mean <= 0.01 and mx <= 0.1, (variant, mean, mx)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: direct comparison where the oracle is affordable, size-independent
+# properties of the domain otherwise
+# ------------------------------------------------------------------------------------------------
+def test_farneback_4k_matches_cv2():
+    from transflow_b200 import ops
+    h, w = 2160, 3840
+    g0, g1 = clip_pair(h, w, seed=11)
+    want = F.farneback(g0, g1)                      # ~2 s on the host
+    got = ops.Farneback(h, w)(dev(g0), dev(g1)).cpu().numpy()
+    mean, mx = epe(got, want)
+    assert mean <= 0.01 and mx <= 0.1, (mean, mx)
+
+
+@pytest.mark.parametrize("shape", [(2160, 3840), (4320, 7680)])
+def test_full_size_properties(shape):
+    """4K / 8K: (1) a uniform integer flow turns the moveref frame into the shifted pixmap and its
+    forward post-process into the negated flow; (2) zero flow is the identity; (3) reset factor 1
+    restores the identity map; (4) Farneback of a frame with itself is exactly zero away from the
+    right / bottom borders (there cv2's "sample outside the image" branch yields a small non-zero
+    flow that spreads by one window per level -- same in the reference)."""
+    from transflow_b200 import ops
+    from transflow_b200.compositor import Compositor
+    from transflow_b200.compositor.pixmap_source_interface import PixmapSourceInterface, StillQueue
+    from transflow_b200.config import LayerConfig
+    h, w = shape
+    rng = np.random.default_rng(3)
+    pix = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    pix_d = dev(pix)
+
+    def make(**kw):
+        comp = Compositor.from_args(h, w, [LayerConfig(0, "moveref", **kw)], background_color="#000000")
+        comp.set_sources({0: [PixmapSourceInterface(StillQueue(pix_d), np.ones((h, w), bool))]})
+        return comp
+    # (2) zero flow
+    comp = make()
+    zero = torch.zeros((h, w, 2), dtype=torch.float32, device="cuda")
+    assert torch.equal(comp.step(zero), pix_d)
+    # (1) uniform backward flow (+3, -2): every pixel takes the record of (x+3, y-2), clipped at the frame
+    fl = torch.zeros((h, w, 2), dtype=torch.float32, device="cuda")
+    fl[..., 0], fl[..., 1] = 3.0, -2.0
+    fl = ops.PostProcess(h, w, False)(fl)
+    out = comp.step(fl)
+    ys = torch.clamp(torch.arange(h, device="cuda") - 2, 0, h - 1)
+    xs = torch.clamp(torch.arange(w, device="cuda") + 3, 0, w - 1)
+    assert torch.equal(out, pix_d[ys][:, xs])
+    comp.layers[0].check_indices()
+    # forward post-process of a uniform flow (+3, -2): target p+f receives origin - target = -(f), elsewhere 0
+    f2 = torch.zeros((h, w, 2), dtype=torch.float32, device="cuda")
+    f2[..., 0], f2[..., 1] = 3.0, -2.0
+    g = ops.PostProcess(h, w, True)(f2)
+    assert torch.all(g[4:-4, 8:-8, 0] == -3.0) and torch.all(g[4:-4, 8:-8, 1] == 2.0)
+    # (3) random reset with factor 1 after a move restores the identity mapping
+    comp = make(reset_mode="random", reset_random_factor=1)
+    assert torch.equal(comp.step(fl), pix_d)
+    del comp
+    # (4) flow of a frame with itself
+    if h <= 2160:
+        g0, _ = clip_pair(h, w, seed=12)
+        a = dev(g0)
+        fb = ops.Farneback(h, w)
+        self_flow = fb(a, a)
+        assert float(self_flow[: h - 300, : w - 300].abs().max()) == 0.0
+        assert float(self_flow.abs().max()) < 0.5

@@ -9,6 +9,7 @@
 // point; window rows slide through registers so every tap is loaded once per pass.
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <vector>
 
 using namespace tf;
@@ -23,6 +24,7 @@ struct LkLevel {
 
 struct tf_lucas_kanade {
     int H, W, win, max_level, step;
+    int variant;  // 0 = warp-per-point tracker (default), 1 = thread-per-point reference kernel
     int gw, gh;  // grid of tracked points
     std::vector<LkLevel> lv;
     float2* next_pts;
@@ -197,6 +199,127 @@ __global__ void __launch_bounds__(128) k_lk_track(const uint8_t* __restrict__ I,
     }
 }
 
+// ---- warp-per-point tracker ---------------------------------------------------------------------
+// One warp tracks one point: the win x win window is spread over the 32 lanes (pixel i -> lane i % 32),
+// each lane keeps the interpolated template (I, dIx, dIy) of its pixels in registers for the whole
+// level, the 2x2 sums are reduced with shuffles, and every lane takes the same convergence branch --
+// so a straggler that needs 30 iterations no longer holds 31 other points hostage, and the template
+// is interpolated once per level instead of once per iteration.  Sums are exact 64-bit integers.
+__device__ __forceinline__ long long lk_warp_sum(long long v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(256) k_lk_track_warp(const uint8_t* __restrict__ I, const uint8_t* __restrict__ J,
+                                                       const short2* __restrict__ D, float2* __restrict__ next_pts,
+                                                       int w, int h, int gw, int gh, int step, int win, int level,
+                                                       int is_top) {
+    const int lane = threadIdx.x & 31;
+    const long long pid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (pid >= (long long)gw * gh) return;
+    const int gy = (int)(pid / gw), gx = (int)(pid - (long long)gy * gw);
+    const float lscale = 1.f / (float)(1 << level);
+    const float half = (float)(win - 1) * 0.5f;
+    float px = (float)(gx * step) * lscale, py = (float)(gy * step) * lscale;
+    float2 np;
+    if (is_top) {
+        np = make_float2(px, py);
+    } else {
+        np = next_pts[pid];
+        np.x *= 2.f;
+        np.y *= 2.f;
+    }
+    if (lane == 0) next_pts[pid] = np;  // stored before any test (points that fail keep this value)
+    px -= half;
+    py -= half;
+    const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+    if (ipx < -win || ipx >= w || ipy < -win || ipy >= h) return;
+    const LkWeights q = lk_weights(px - (float)ipx, py - (float)ipy);
+    const bool insideI = ipx >= 0 && ipy >= 0 && ipx + win < w && ipy + win < h;
+    const int npx = win * win;
+    const float FLT_SCALE = 1.f / (float)(1 << 20);
+
+    // template of this lane's pixels + covariance of the interpolated derivatives
+    int ival[KMAX];
+    short2 dval[KMAX];
+    int wx[KMAX], wy[KMAX];
+    long long a11 = 0, a12 = 0, a22 = 0;
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) {
+        int i = lane + 32 * k;
+        ival[k] = 0;
+        dval[k] = make_short2(0, 0);
+        wx[k] = wy[k] = 0;
+        if (i < npx) {
+            int y = i / win, x = i - y * win;
+            wx[k] = x;
+            wy[k] = y;
+            int X = ipx + x, Y = ipy + y;
+            int i00 = lk_img(I, X, Y, w, h, insideI), i01 = lk_img(I, X + 1, Y, w, h, insideI);
+            int i10 = lk_img(I, X, Y + 1, w, h, insideI), i11 = lk_img(I, X + 1, Y + 1, w, h, insideI);
+            short2 d00 = lk_der(D, X, Y, w, h, insideI), d01 = lk_der(D, X + 1, Y, w, h, insideI);
+            short2 d10 = lk_der(D, X, Y + 1, w, h, insideI), d11 = lk_der(D, X + 1, Y + 1, w, h, insideI);
+            ival[k] = lk_descale(i00 * q.w00 + i01 * q.w01 + i10 * q.w10 + i11 * q.w11, LK_W_BITS - 5);
+            int ixv = lk_descale(d00.x * q.w00 + d01.x * q.w01 + d10.x * q.w10 + d11.x * q.w11, LK_W_BITS);
+            int iyv = lk_descale(d00.y * q.w00 + d01.y * q.w01 + d10.y * q.w10 + d11.y * q.w11, LK_W_BITS);
+            dval[k] = make_short2((short)ixv, (short)iyv);
+            a11 += (long long)(ixv * ixv);
+            a12 += (long long)(ixv * iyv);
+            a22 += (long long)(iyv * iyv);
+        }
+    }
+    float A11 = (float)lk_warp_sum(a11) * FLT_SCALE, A12 = (float)lk_warp_sum(a12) * FLT_SCALE,
+          A22 = (float)lk_warp_sum(a22) * FLT_SCALE;
+    float Dd = A11 * A22 - A12 * A12;
+    float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+    if (minEig < 1e-4f || Dd < 1.1920929e-07f) return;
+    Dd = 1.f / Dd;
+
+    float nx = np.x - half, ny = np.y - half;
+    float pdx = 0.f, pdy = 0.f;
+    for (int j = 0; j < 30; j++) {
+        int inx = (int)floorf(nx), iny = (int)floorf(ny);
+        if (inx < -win || inx >= w || iny < -win || iny >= h) break;
+        LkWeights r = lk_weights(nx - (float)inx, ny - (float)iny);
+        const bool insideJ = inx >= 0 && iny >= 0 && inx + win < w && iny + win < h;
+        long long b1 = 0, b2 = 0;
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) {
+            if (lane + 32 * k < npx) {
+                int X = inx + wx[k], Y = iny + wy[k];
+                int j00, j01, j10, j11;
+                if (insideJ) {
+                    const uint8_t* p = J + (size_t)Y * w + X;
+                    j00 = __ldg(p); j01 = __ldg(p + 1); j10 = __ldg(p + w); j11 = __ldg(p + w + 1);
+                } else {
+                    j00 = lk_img(J, X, Y, w, h, false); j01 = lk_img(J, X + 1, Y, w, h, false);
+                    j10 = lk_img(J, X, Y + 1, w, h, false); j11 = lk_img(J, X + 1, Y + 1, w, h, false);
+                }
+                int diff = lk_descale(j00 * r.w00 + j01 * r.w01 + j10 * r.w10 + j11 * r.w11, LK_W_BITS - 5) - ival[k];
+                b1 += (long long)(diff * (int)dval[k].x);
+                b2 += (long long)(diff * (int)dval[k].y);
+            }
+        }
+        float fb1 = (float)lk_warp_sum(b1) * FLT_SCALE, fb2 = (float)lk_warp_sum(b2) * FLT_SCALE;
+        float dx = (A12 * fb2 - A22 * fb1) * Dd, dy = (A12 * fb1 - A11 * fb2) * Dd;
+        nx += dx;
+        ny += dy;
+        float2 o = make_float2(nx + half, ny + half);
+        bool stop = (double)dx * dx + (double)dy * dy <= 1e-4;  // epsilon^2, epsilon = 0.01
+        if (!stop && j > 0 && fabsf(dx + pdx) < 0.01f && fabsf(dy + pdy) < 0.01f) {
+            o.x -= dx * 0.5f;
+            o.y -= dy * 0.5f;
+            stop = true;
+        }
+        if (lane == 0) next_pts[pid] = o;
+        if (stop) break;
+        pdx = dx;
+        pdy = dy;
+    }
+}
+
 // flow = p1 - p0, block-replicated (numpy.kron) back to (H, W), optional final clip
 __global__ void __launch_bounds__(256) k_lk_flow_out(const float2* __restrict__ next_pts, float2* __restrict__ flow,
                                                      int H, int W, int gw, int step, int clip) {
@@ -237,6 +360,10 @@ extern "C" int tf_lk_create(tf_lucas_kanade** out, int height, int width, int wi
     tf_lucas_kanade* h = new (std::nothrow) tf_lucas_kanade();
     TF_REQUIRE(h, TF_ERR_CUDA, "out of host memory");
     h->H = height; h->W = width; h->win = win_size; h->max_level = max_level; h->step = step;
+    {
+        const char* v = getenv("TFB200_LK_VARIANT");
+        h->variant = v ? atoi(v) : 0;
+    }
     h->gw = ceil_div(width, step);
     h->gh = ceil_div(height, step);
     h->next_pts = nullptr;
@@ -285,12 +412,23 @@ extern "C" int tf_lk_run(tf_lucas_kanade* h, const uint8_t* left, const uint8_t*
     }
     int top = (int)h->lv.size() - 1;
     dim3 tgrid(ceil_div(h->gw, 32), ceil_div(h->gh, 4));
+    long long npoints = (long long)h->gw * h->gh;
+    unsigned wgrid = (unsigned)((npoints + 7) / 8);
+    int kmax = ceil_div(h->win * h->win, 32);
     for (int l = top; l >= 0; l--) {
         LkLevel& L = h->lv[l];
         {
             ScopedKernelTimer timer(l == 0 ? TFK_LK_TRACK_FINEST : -1, st);
-            k_lk_track<<<tgrid, 128, 0, st>>>(L.img[0], L.img[1], L.deriv, h->next_pts, L.w, L.h, h->gw, h->gh, h->step,
-                                              h->win, l, l == top);
+#define TF_LKW(K)                                                                                                  \
+    k_lk_track_warp<K><<<wgrid, 256, 0, st>>>(L.img[0], L.img[1], L.deriv, h->next_pts, L.w, L.h, h->gw, h->gh, h->step, \
+                                              h->win, l, l == top)
+            if (h->variant == 1 || kmax > 31)   // thread-per-point reference kernel (and very large windows)
+                k_lk_track<<<tgrid, 128, 0, st>>>(L.img[0], L.img[1], L.deriv, h->next_pts, L.w, L.h, h->gw, h->gh,
+                                                  h->step, h->win, l, l == top);
+            else if (kmax <= 8) TF_LKW(8);
+            else if (kmax <= 14) TF_LKW(14);
+            else TF_LKW(31);
+#undef TF_LKW
         }
         TF_LAUNCHED();
     }
