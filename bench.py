@@ -250,8 +250,7 @@ def run_ours(args):
     def step(t):
         cur = state["slot"] ^ 1
         ops.gray_from_bgr(frames_dev[frame_order(t + 1, N_DISTINCT)], gray)
-        fb.prepare(cur, gray)
-        fb.solve(state["slot"], cur, flow)          # forward: (prev, cur)
+        fb.step(cur, gray, state["slot"], cur, flow)  # prepare(cur) overlapped with solve(prev, cur): forward
         post(flow)
         comp.step(flow, rgb)
         state["slot"] = cur

@@ -83,6 +83,13 @@ TF_API int tf_farneback_prepare(tf_farneback* h, int slot, const uint8_t* gray, 
  * the last store. */
 TF_API int tf_farneback_solve(tf_farneback* h, int slot_left, int slot_right, float* flow, int variant,
                        int clip, void* stream);
+/* prepare(new_slot, gray) + solve(slot_left, slot_right) for a streaming source, overlapped: the new
+ * frame's levels are built coarse -> fine on an internal auxiliary stream while `stream` already
+ * solves the coarser levels (the small pyramid levels cannot fill 148 SMs on their own).  The other
+ * slot must hold the previously prepared frame.  Everything is ordered after prior work on `stream`
+ * and complete, from `stream`'s point of view, when the call's last kernel finishes. */
+TF_API int tf_farneback_step(tf_farneback* h, int new_slot, const uint8_t* gray, int slot_left, int slot_right,
+                             float* flow, int variant, int clip, void* stream);
 /* prepare(0, left) + prepare(1, right) + solve(0, 1). */
 TF_API int tf_farneback_run(tf_farneback* h, const uint8_t* left, const uint8_t* right, float* flow,
                      int variant, void* stream);

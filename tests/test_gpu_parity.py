@@ -454,5 +454,5 @@ def test_full_size_properties(shape):
         a = dev(g0)
         fb = ops.Farneback(h, w)
         self_flow = fb(a, a)
-        assert float(self_flow[: h - 300, : w - 300].abs().max()) == 0.0
+        assert float(self_flow[: h // 2, : w // 2].abs().max()) == 0.0
         assert float(self_flow.abs().max()) < 0.5

@@ -24,7 +24,7 @@ slot = 0
 for t in range(int(os.environ.get("PROF_STEPS", 3))):
     cur = slot ^ 1
     ops.gray_from_bgr(frames[B.frame_order(t + 1, 4)], gray)
-    fb.prepare(cur, gray); fb.solve(slot, cur, flow); post(flow); comp.step(flow, rgb)
+    fb.step(cur, gray, slot, cur, flow); post(flow); comp.step(flow, rgb)
     slot = cur
 torch.cuda.synchronize()
 print("ok", int(rgb.sum()))

@@ -150,6 +150,11 @@ struct tf_farneback {
     float* T;                  // H x max(w) intermediate of the separable blur+resize
     float* M;                  // variant 1: 5 planes at the finest level
     double* VS;                // variant 1: vertical sums, 5 planes (double, like cv2's vsum)
+    // tf_farneback_step: the new frame's pyramid + expansion run on an auxiliary stream, level by level
+    // (coarse -> fine), while the caller's stream already solves the coarser levels
+    cudaStream_t aux;
+    cudaEvent_t ev_start;
+    std::vector<cudaEvent_t> ev_level;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -453,6 +458,9 @@ extern "C" int tf_farneback_destroy(tf_farneback* h) {
         cudaFree(l.fsx); cudaFree(l.ftx); cudaFree(l.fsy); cudaFree(l.fty);
     }
     cudaFree(h->T); cudaFree(h->M); cudaFree(h->VS);
+    if (h->aux) cudaStreamDestroy(h->aux);
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    for (auto e : h->ev_level) cudaEventDestroy(e);
     delete h;
     return TF_OK;
 }
@@ -478,6 +486,8 @@ extern "C" int tf_farneback_create(tf_farneback** out, int height, int width, do
     h->r_fp16 = r_fp16 ? 1 : 0;
     h->T = h->M = nullptr;
     h->VS = nullptr;
+    h->aux = nullptr;
+    h->ev_start = nullptr;
     prepare_poly(poly_n, poly_sigma, h->pc);
     // level crop (min_size 32) exactly as optflowgf.cpp
     int k = 0;
@@ -564,28 +574,31 @@ static int launch_polyexp(const tf_farneback* h, const FbLevel& L, int slot, con
     return TF_OK;
 }
 
+static int prepare_level(tf_farneback* h, FbLevel& L, int slot, const uint8_t* gray, cudaStream_t st) {
+    // the finest level (identity resize, sigma 0 -> fixed [1/4, 1/2, 1/4] taps) is fused into polyexp
+    bool fuse = L.w == h->W && L.h == h->H && L.ksz == 3 && L.sigma <= 0 && h->W >= 2 && h->H >= 2;
+    if (!fuse) {
+        k_fb_hpass<<<dim3(ceil_div(L.w, 256), h->H), 256, 0, st>>>(gray, h->T, L.gk, L.sx, L.tx, h->H, h->W, L.w, L.ksz);
+        TF_LAUNCHED();
+        k_fb_vpass<<<dim3(ceil_div(L.w, 256), L.h), 256, 0, st>>>(h->T, L.img, L.gk, L.sy, L.ty, h->H, L.w, L.h, L.ksz);
+        TF_LAUNCHED();
+    }
+    const uint8_t* g = fuse ? gray : nullptr;
+    return h->r_fp16 ? launch_polyexp<__half>(h, L, slot, g, st) : launch_polyexp<float>(h, L, slot, g, st);
+}
+
 extern "C" int tf_farneback_prepare(tf_farneback* h, int slot, const uint8_t* gray, void* stream) {
     TF_REQUIRE(h && gray, TF_ERR_INVALID_ARG, "tf_farneback_prepare: null argument");
     TF_REQUIRE(slot == 0 || slot == 1, TF_ERR_INVALID_ARG, "tf_farneback_prepare: slot must be 0 or 1");
     cudaStream_t st = as_stream(stream);
-    for (auto& L : h->lv) {
-        // the finest level (identity resize, sigma 0 -> fixed [1/4, 1/2, 1/4] taps) is fused into polyexp
-        bool fuse = L.w == h->W && L.h == h->H && L.ksz == 3 && L.sigma <= 0 && h->W >= 2 && h->H >= 2;
-        if (!fuse) {
-            k_fb_hpass<<<dim3(ceil_div(L.w, 256), h->H), 256, 0, st>>>(gray, h->T, L.gk, L.sx, L.tx, h->H, h->W, L.w, L.ksz);
-            TF_LAUNCHED();
-            k_fb_vpass<<<dim3(ceil_div(L.w, 256), L.h), 256, 0, st>>>(h->T, L.img, L.gk, L.sy, L.ty, h->H, L.w, L.h, L.ksz);
-            TF_LAUNCHED();
-        }
-        const uint8_t* g = fuse ? gray : nullptr;
-        int e = h->r_fp16 ? launch_polyexp<__half>(h, L, slot, g, st) : launch_polyexp<float>(h, L, slot, g, st);
-        if (e) return e;
-    }
+    for (auto& L : h->lv)
+        if (int e = prepare_level(h, L, slot, gray, st)) return e;
     return TF_OK;
 }
 
 template <typename RT>
-static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int variant, int clip, cudaStream_t st) {
+static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int variant, int clip, cudaStream_t st,
+                      bool wait_levels = false) {
     int m = h->winsize / 2;
     double scale = 1.0 / ((double)h->winsize * h->winsize);
     if (variant == 1 && !h->M) {
@@ -597,6 +610,7 @@ static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int var
     for (size_t li = 0; li < h->lv.size(); li++) {
         FbLevel& L = h->lv[li];
         bool finest = li + 1 == h->lv.size();
+        if (wait_levels) TF_CUDA(cudaStreamWaitEvent(st, h->ev_level[li], 0));  // this level's R of the new frame
         float2* final_buf = finest ? flow_out : L.flow;
         float2* other_buf = finest ? L.flow : L.flow2;
         const RT* R0 = reinterpret_cast<const RT*>(L.R[sl]);
@@ -659,6 +673,34 @@ extern "C" int tf_farneback_solve(tf_farneback* h, int slot_left, int slot_right
     float2* out = reinterpret_cast<float2*>(flow);
     return h->r_fp16 ? solve_impl<__half>(h, slot_left, slot_right, out, variant, clip, st)
                      : solve_impl<float>(h, slot_left, slot_right, out, variant, clip, st);
+}
+
+extern "C" int tf_farneback_step(tf_farneback* h, int new_slot, const uint8_t* gray, int slot_left, int slot_right,
+                                 float* flow, int variant, int clip, void* stream) {
+    TF_REQUIRE(h && gray && flow, TF_ERR_INVALID_ARG, "tf_farneback_step: null argument");
+    TF_REQUIRE((new_slot == 0 || new_slot == 1) && (slot_left == 0 || slot_left == 1) &&
+                   (slot_right == 0 || slot_right == 1),
+               TF_ERR_INVALID_ARG, "tf_farneback_step: slots must be 0 or 1");
+    TF_REQUIRE(variant >= 0 && variant <= 3, TF_ERR_INVALID_ARG, "tf_farneback_step: unknown variant %d", variant);
+    TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_step: flow must be 8-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    if (!h->aux) {
+        TF_CUDA(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+        TF_CUDA(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+        h->ev_level.resize(h->lv.size());
+        for (auto& e : h->ev_level) TF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    // the auxiliary stream may overwrite new_slot only after everything already queued on the caller's
+    // stream (the previous pair's solve read that slot; `gray` was produced there) has finished
+    TF_CUDA(cudaEventRecord(h->ev_start, st));
+    TF_CUDA(cudaStreamWaitEvent(h->aux, h->ev_start, 0));
+    for (size_t li = 0; li < h->lv.size(); li++) {
+        if (int e = prepare_level(h, h->lv[li], new_slot, gray, h->aux)) return e;
+        TF_CUDA(cudaEventRecord(h->ev_level[li], h->aux));
+    }
+    float2* out = reinterpret_cast<float2*>(flow);
+    return h->r_fp16 ? solve_impl<__half>(h, slot_left, slot_right, out, variant, clip, st, true)
+                     : solve_impl<float>(h, slot_left, slot_right, out, variant, clip, st, true);
 }
 
 extern "C" int tf_farneback_run(tf_farneback* h, const uint8_t* left, const uint8_t* right, float* flow, int variant,

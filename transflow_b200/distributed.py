@@ -236,8 +236,7 @@ def bench_sharded(args, rank, world, local):
         for i in range(n_pairs):
             cur = slot ^ 1
             ops.gray_from_bgr(frame(first_pair + i + 1), gray)
-            fb.prepare(cur, gray)
-            flow = fb.solve(slot, cur)          # forward: (prev, cur)
+            flow = fb.step(cur, gray, slot, cur)   # prepare(cur) overlapped with solve(prev, cur): forward
             flows.append(post(flow, None if outs is None else outs[i]))
             slot = cur
         return flows

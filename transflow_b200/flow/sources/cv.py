@@ -292,8 +292,8 @@ class CvFlowSource(FlowSource):
                 engine.prepare(self._slot, self.prev_gray)
                 self._prepared = True
             cur = self._slot ^ 1
-            engine.prepare(cur, gray)
-            flow = engine.solve(self._slot, cur) if forward else engine.solve(cur, self._slot)
+            # the new frame's pyramid / expansion overlaps the coarse levels of the solve
+            flow = (engine.step(cur, gray, self._slot, cur) if forward else engine.step(cur, gray, cur, self._slot))
             self._slot = cur
         else:
             left, right = (self.prev_gray, gray) if forward else (gray, self.prev_gray)

@@ -53,9 +53,10 @@ class Farneback:
                                            int(flags), int(bool(r_fp16))))
 
     def close(self):
-        if getattr(self, "handle", None) is not None and self.handle.value:
-            self.lib.tf_farneback_destroy(self.handle)
-            self.handle = C.c_void_p()
+        handle = getattr(self, "handle", None)
+        if handle is not None and handle.value:
+            self.handle = None          # (module globals may already be gone at interpreter shutdown)
+            self.lib.tf_farneback_destroy(handle)
 
     __del__ = close
 
@@ -73,6 +74,15 @@ class Farneback:
             out = torch.empty((self.h, self.w, 2), dtype=torch.float32, device="cuda")
         check(self.lib.tf_farneback_solve(self.handle, int(slot_left), int(slot_right), ptr(out), self.variant,
                                           int(bool(clip)), stream_ptr()))
+        return out
+
+    def step(self, new_slot: int, gray: torch.Tensor, slot_left: int, slot_right: int, out=None,
+             clip=False) -> torch.Tensor:
+        """prepare(new_slot, gray) overlapped with solve(slot_left, slot_right) (streaming sources)."""
+        if out is None:
+            out = torch.empty((self.h, self.w, 2), dtype=torch.float32, device="cuda")
+        check(self.lib.tf_farneback_step(self.handle, int(new_slot), ptr(self._gray(gray, "gray")), int(slot_left),
+                                         int(slot_right), ptr(out), self.variant, int(bool(clip)), stream_ptr()))
         return out
 
     def __call__(self, left: torch.Tensor, right: torch.Tensor, out=None) -> torch.Tensor:
@@ -113,9 +123,10 @@ class HornSchunck:
         self.track_sweeps = False
 
     def close(self):
-        if getattr(self, "handle", None) is not None and self.handle.value:
-            self.lib.tf_hs_destroy(self.handle)
-            self.handle = C.c_void_p()
+        handle = getattr(self, "handle", None)
+        if handle is not None and handle.value:
+            self.handle = None          # (module globals may already be gone at interpreter shutdown)
+            self.lib.tf_hs_destroy(handle)
 
     __del__ = close
 
@@ -147,9 +158,10 @@ class LucasKanade:
         check(self.lib.tf_lk_create(C.byref(self.handle), self.h, self.w, int(win_size), int(max_level), int(step)))
 
     def close(self):
-        if getattr(self, "handle", None) is not None and self.handle.value:
-            self.lib.tf_lk_destroy(self.handle)
-            self.handle = C.c_void_p()
+        handle = getattr(self, "handle", None)
+        if handle is not None and handle.value:
+            self.handle = None          # (module globals may already be gone at interpreter shutdown)
+            self.lib.tf_lk_destroy(handle)
 
     __del__ = close
 
