@@ -131,7 +131,7 @@ struct FbLevel {
     int* sy;
     float* ty;
     float* img;     // pyramid image of the frame prepared last (h x w)
-    void* R[2];     // polynomial expansion per slot: 5 planes of h*w (float or __half)
+    void* R[2];     // polynomial expansion per slot, 5*h*w elements (float or __half) in the "4+1" layout
     float2* flow;   // per-level flow (the finest level writes into the caller's buffer)
     float2* flow2;  // ping-pong partner for the fused iteration kernel
     int* fsx;       // resize tables mapping the next-coarser level's flow onto this level
@@ -349,17 +349,17 @@ __global__ void __launch_bounds__(256) k_fb_polyexp(const float* __restrict__ im
         int x = x0 + gx;
         if (y < h) {
             size_t at = (size_t)y * w + x;
-            if (sizeof(RT) == 4 && x + 4 <= w && (w & 3) == 0) {
+            // "4+1" layout: one 128-bit store per pixel for the first four coefficients
 #pragma unroll
-                for (int c = 0; c < 5; c++)
-                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(R) + c * plane + at) =
-                        make_float4(out[c][0], out[c][1], out[c][2], out[c][3]);
+            for (int o = 0; o < 4; o++)
+                if (x + o < w) store_quad(R, at + o, make_float4(out[0][o], out[1][o], out[2][o], out[3][o]));
+            if (sizeof(RT) == 4 && x + 4 <= w && (w & 3) == 0) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(R) + 4 * plane + at) =
+                    make_float4(out[4][0], out[4][1], out[4][2], out[4][3]);
             } else {
 #pragma unroll
-                for (int c = 0; c < 5; c++)
-#pragma unroll
-                    for (int o = 0; o < 4; o++)
-                        if (x + o < w) store_r(R + c * plane + at + o, out[c][o]);
+                for (int o = 0; o < 4; o++)
+                    if (x + o < w) store_c4(R, plane, at + o, out[4][o]);
             }
         }
     }
@@ -710,9 +710,17 @@ extern "C" int tf_farneback_run(tf_farneback* h, const uint8_t* left, const uint
     return tf_farneback_solve(h, 0, 1, flow, variant, 0, stream);
 }
 
-__global__ void __launch_bounds__(256) k_half_to_float(const __half* __restrict__ in, float* __restrict__ out, size_t n) {
+// test hook: "4+1" storage -> five float planes (5, h, w)
+template <typename RT>
+__global__ void __launch_bounds__(256) k_r_to_planes(const RT* __restrict__ R, float* __restrict__ out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = __half2float(in[i]);
+    if (i >= n) return;
+    float4 q = load_quad(R, i);
+    out[i] = q.x;
+    out[n + i] = q.y;
+    out[2 * n + i] = q.z;
+    out[3 * n + i] = q.w;
+    out[4 * n + i] = load_c4(R, n, i);
 }
 
 extern "C" int tf_farneback_debug_read(tf_farneback* h, int slot, int li, int what, float* out, void* stream) {
@@ -725,13 +733,12 @@ extern "C" int tf_farneback_debug_read(tf_farneback* h, int slot, int li, int wh
     if (what == 0) {
         TF_CUDA(cudaMemcpyAsync(out, L.img, n * 4, cudaMemcpyDeviceToDevice, st));
     } else if (what == 1) {
-        if (h->r_fp16) {
-            k_half_to_float<<<(unsigned)((n * 5 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __half*>(L.R[slot]),
-                                                                           out, n * 5);
-            TF_LAUNCHED();
-        } else {
-            TF_CUDA(cudaMemcpyAsync(out, L.R[slot], n * 20, cudaMemcpyDeviceToDevice, st));
-        }
+        unsigned blocks = (unsigned)((n + 255) / 256);
+        if (h->r_fp16)
+            k_r_to_planes<__half><<<blocks, 256, 0, st>>>(reinterpret_cast<const __half*>(L.R[slot]), out, n);
+        else
+            k_r_to_planes<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(L.R[slot]), out, n);
+        TF_LAUNCHED();
     } else if (what == 2) {
         TF_REQUIRE(li + 1 < (int)h->lv.size(), TF_ERR_INVALID_ARG,
                    "tf_farneback_debug_read: the finest level's flow is the solve output");

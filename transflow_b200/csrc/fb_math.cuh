@@ -13,20 +13,45 @@ struct PolyCoef {
     float ig11, ig03, ig33, ig55;
 };
 
-__device__ __forceinline__ void store_r(float* p, float v) { *p = v; }
-__device__ __forceinline__ void store_r(__half* p, float v) { *p = __float2half_rn(v); }
-__device__ __forceinline__ float load_r(const float* p) { return __ldg(p); }
-__device__ __forceinline__ float load_r(const __half* p) { return __half2float(__ldg(p)); }
+// R (polynomial expansion) storage layout "4+1" for an image of n = w*h pixels and element type RT:
+//   elements [0, 4n)  : (d/dy, d/dx, yy, xx) interleaved per pixel -> one 128-bit (fp32) load per tap
+//   elements [4n, 5n) : xy plane
+__device__ __forceinline__ float4 load_quad(const float* R, size_t px) {
+    return __ldg(reinterpret_cast<const float4*>(R) + px);
+}
+__device__ __forceinline__ float4 load_quad(const __half* R, size_t px) {
+    uint2 raw = __ldg(reinterpret_cast<const uint2*>(R) + px);
+    float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float load_c4(const float* R, size_t plane, size_t px) { return __ldg(R + 4 * plane + px); }
+__device__ __forceinline__ float load_c4(const __half* R, size_t plane, size_t px) {
+    return __half2float(__ldg(R + 4 * plane + px));
+}
+__device__ __forceinline__ void store_quad(float* R, size_t px, float4 v) { reinterpret_cast<float4*>(R)[px] = v; }
+__device__ __forceinline__ void store_quad(__half* R, size_t px, float4 v) {
+    __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    uint2 raw;
+    raw.x = *reinterpret_cast<unsigned*>(&lo);
+    raw.y = *reinterpret_cast<unsigned*>(&hi);
+    reinterpret_cast<uint2*>(R)[px] = raw;
+}
+__device__ __forceinline__ void store_c4(float* R, size_t plane, size_t px, float v) { R[4 * plane + px] = v; }
+__device__ __forceinline__ void store_c4(__half* R, size_t plane, size_t px, float v) {
+    R[4 * plane + px] = __float2half_rn(v);
+}
 
 __device__ __forceinline__ float fb_border(int d) { return d < 2 ? 0.14f : 0.4472f; }
 
 // FarnebackUpdateMatrices for one pixel: R0 at (x, y) (already loaded into a[5]), R1 sampled
 // bilinearly at (x+dx, y+dy) (falls back to R0 only when the sample leaves the image), 5-px border
-// attenuation.  R planes are ordered (d/dy, d/dx, yy, xx, xy), each w*h elements.
+// attenuation.  Coefficients are ordered (d/dy, d/dx, yy, xx, xy), stored "4+1" (see above).
 template <typename RT>
 __device__ __forceinline__ void fb_load_r0(const RT* __restrict__ R0, size_t plane, size_t at, float* a) {
-#pragma unroll
-    for (int c = 0; c < 5; c++) a[c] = load_r(R0 + c * plane + at);
+    float4 q = load_quad(R0, at);
+    a[0] = q.x; a[1] = q.y; a[2] = q.z; a[3] = q.w;
+    a[4] = load_c4(R0, plane, at);
 }
 
 template <typename RT>
@@ -41,16 +66,15 @@ __device__ __forceinline__ void fb_update_matrix_pre(const float* a, const RT* _
     float r2, r3, r4, r5, r6;
     if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
         float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-        const RT* p = R1 + ((size_t)y1 * w + x1);
-        r2 = a00 * load_r(p) + a01 * load_r(p + 1) + a10 * load_r(p + w) + a11 * load_r(p + w + 1);
-        p += plane;
-        r3 = a00 * load_r(p) + a01 * load_r(p + 1) + a10 * load_r(p + w) + a11 * load_r(p + w + 1);
-        p += plane;
-        r4 = a00 * load_r(p) + a01 * load_r(p + 1) + a10 * load_r(p + w) + a11 * load_r(p + w + 1);
-        p += plane;
-        r5 = a00 * load_r(p) + a01 * load_r(p + 1) + a10 * load_r(p + w) + a11 * load_r(p + w + 1);
-        p += plane;
-        r6 = a00 * load_r(p) + a01 * load_r(p + 1) + a10 * load_r(p + w) + a11 * load_r(p + w + 1);
+        const size_t q = (size_t)y1 * w + x1;
+        float4 q00 = load_quad(R1, q), q01 = load_quad(R1, q + 1), q10 = load_quad(R1, q + w), q11 = load_quad(R1, q + w + 1);
+        float e00 = load_c4(R1, plane, q), e01 = load_c4(R1, plane, q + 1), e10 = load_c4(R1, plane, q + w),
+              e11 = load_c4(R1, plane, q + w + 1);
+        r2 = a00 * q00.x + a01 * q01.x + a10 * q10.x + a11 * q11.x;
+        r3 = a00 * q00.y + a01 * q01.y + a10 * q10.y + a11 * q11.y;
+        r4 = a00 * q00.z + a01 * q01.z + a10 * q10.z + a11 * q11.z;
+        r5 = a00 * q00.w + a01 * q01.w + a10 * q10.w + a11 * q11.w;
+        r6 = a00 * e00 + a01 * e01 + a10 * e10 + a11 * e11;
         r4 = (a[2] + r4) * 0.5f;
         r5 = (a[3] + r5) * 0.5f;
         r6 = (a[4] + r6) * 0.25f;

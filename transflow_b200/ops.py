@@ -41,11 +41,13 @@ class Farneback:
     """Device Farneback flow with the parameters of ``CvFlowConfig.fb_*`` (cv.py:275-281)."""
 
     def __init__(self, height, width, pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5,
-                 poly_sigma=1.2, flags=0, r_fp16=False, variant=None):
+                 poly_sigma=1.2, flags=0, r_fp16=None, variant=None):
         self.lib = _lib.load()
         self.h, self.w = int(height), int(width)
         if variant is None:
             variant = int(os.environ.get("TFB200_FB_VARIANT", DEFAULT_FB_VARIANT))
+        if r_fp16 is None:      # half-precision STORAGE of the polynomial expansion (compute stays fp32)
+            r_fp16 = bool(int(os.environ.get("TFB200_R_FP16", "0")))
         self.variant = int(variant)
         self.handle = C.c_void_p()
         check(self.lib.tf_farneback_create(C.byref(self.handle), self.h, self.w, float(pyr_scale), int(levels),
