@@ -202,13 +202,23 @@ static int fb_launch_tile(const RT* R0, const RT* R1, const float2* in, float2* 
         TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
         attr_set = true;
     }
-    // CTAs are scheduled dynamically, so aim for ~4.5 waves of short CTAs: the tail costs about half a
-    // CTA instead of a partially filled wave; the price is the 2m-row vertical halo per chunk
-    int per_sm = std::max(1, std::min(2, (int)((227 * 1024) / (G::SMEM + 1024))));
+    // Chunk height: a CTA costs about (rows + 2m) matrix rows (the vertical halo is paid once per chunk)
+    // and the CTAs resident on one SM share its throughput, so the kernel takes about
+    // (CTAs per SM) x (rows + 2m): whole CTAs while the grid is under two per SM, CTAs/SMs plus half a CTA
+    // of tail once the hardware scheduler can balance.  Pick the cheapest multiple of the tile height.
     int strips = ceil_div(w, FBT_TX);
-    int slots = per_sm * sm_count();
-    int rows = (int)((double)h * strips / (4.5 * slots) / FBT_TY + 0.5) * FBT_TY;
-    rows = std::max(2 * FBT_TY, std::min(rows, ceil_div(h, FBT_TY) * FBT_TY));
+    int sms = sm_count();
+    int rows = FBT_TY;
+    double best = 1e30;
+    for (int r = FBT_TY; r < h + FBT_TY; r += FBT_TY) {
+        int ctas = strips * ceil_div(h, r);
+        double per_sm = ctas <= 2 * sms ? (double)ceil_div(ctas, sms) : (double)ctas / sms + 0.5;
+        double cost = per_sm * (std::min(r, h) + 2 * MR);
+        if (cost < best) {
+            best = cost;
+            rows = r;
+        }
+    }
     dim3 grid(strips, ceil_div(h, rows));
     kern<<<grid, FBT_NT, G::SMEM, st>>>(R0, R1, in, dst, w, h, scale, rows, clip);
     return TF_OK;
