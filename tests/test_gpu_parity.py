@@ -456,3 +456,43 @@ def test_full_size_properties(shape):
         self_flow = fb(a, a)
         assert float(self_flow[: h // 2, : w // 2].abs().max()) == 0.0
         assert float(self_flow.abs().max()) < 0.5
+
+
+@pytest.mark.parametrize("rgba_pixmap", [False, True])
+@pytest.mark.parametrize("reset", ["off", "random"])
+def test_moveref_fast_path_equals_generic_kernel(reset, rgba_pixmap, tmp_path):
+    """The specialised single-source kernel (device Philox draws, fp32 threshold test with exact
+    fallback) must produce the same state and frames as the generic kernel, which is itself pinned to
+    the reference by the golden cases.  `mask_alpha=ones` forces the generic path without changing
+    the semantics."""
+    from transflow_b200.compositor import Compositor
+    from transflow_b200.compositor.pixmap_source_interface import PixmapSourceInterface, StillQueue
+    from transflow_b200.config import LayerConfig
+    from transflow_b200.synthetic import radial_mask
+    import PIL.Image
+    h, w = 270, 484
+    rng = np.random.default_rng(21)
+    pix = rng.integers(0, 256, (h, w, 4 if rgba_pixmap else 3), dtype=np.uint8)
+    if rgba_pixmap:
+        pix[..., 3] = np.where(rng.random((h, w)) < 0.3, 0, pix[..., 3])
+    mask_png = str(tmp_path / "m.png")
+    PIL.Image.fromarray(np.rint(radial_mask(h, w) * 255).astype(np.uint8)).save(mask_png)
+    kw = dict(reset_mode=reset, reset_random_factor=0.5, reset_mask=mask_png if reset == "random" else None)
+    comps = []
+    for force_generic in (False, True):
+        cfg = LayerConfig(0, "moveref", mask_alpha="ones" if force_generic else None, **kw)
+        c = Compositor.from_args(h, w, [cfg], background_color="#123456")
+        c.set_sources({0: [PixmapSourceInterface(StillQueue(dev(pix)), np.ones((h, w), bool))]})
+        comps.append(c)
+    for t in range(5):
+        flow = F.post_process(rng.uniform(-5, 5, (h, w, 2)).astype(np.float32), False)
+        flow[rng.random((h, w)) < 0.2] = 0
+        a, b = (c.step(flow).cpu().numpy() for c in comps)
+        np.testing.assert_array_equal(a, b, err_msg=f"frame {t}")
+        np.testing.assert_array_equal(comps[0].layers[0].data, comps[1].layers[0].data, err_msg=f"data {t}")
+        np.testing.assert_array_equal(comps[0].layers[0].rgba, comps[1].layers[0].rgba, err_msg=f"rgba {t}")
+    if reset == "random":
+        d = comps[0].layers[0].data
+        base = np.indices((h, w), dtype=np.int32).transpose(1, 2, 0)
+        frac = (d[..., :2] == base).all(axis=-1).mean()
+        assert 0.05 < frac < 0.9          # some pixels were reset, not all

@@ -57,13 +57,14 @@ struct LayerParams {
     int do_introduce;
 };
 
-// ---- Philox4x32-10 (counter = pixel pair, key = seed; frame in the counter): throughput-mode reset
-// draws.  One call yields 128 bits = two 53-bit uniforms, so a pixel pair shares one evaluation.
-__device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t frame, uint32_t ctr) {
+// ---- Philox4x32-7 (counter = pixel pair, key = seed; frame in the counter): throughput-mode reset
+// draws (7 rounds is the smallest variant that passes BigCrush; this is a visual effect, not
+// cryptography).  One call yields 128 bits = two 53-bit uniforms, so a pixel pair shares one evaluation.
+__device__ __forceinline__ uint4 philox4x32_7(uint64_t seed, uint64_t frame, uint32_t ctr) {
     uint32_t c0 = ctr, c1 = (uint32_t)frame, c2 = (uint32_t)(frame >> 32), c3 = 0x7f4a7c15u;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < 7; r++) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
@@ -74,7 +75,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t frame, ui
 }
 
 __device__ __forceinline__ double philox_uniform53(uint64_t seed, uint64_t frame, uint32_t pixel) {
-    uint4 r = philox4x32_10(seed, frame, pixel >> 1);
+    uint4 r = philox4x32_7(seed, frame, pixel >> 1);
     uint32_t a = (pixel & 1) ? r.z : r.x, b = (pixel & 1) ? r.w : r.y;
     // same 53-bit construction as numpy's random_sample: (a >> 5) * 2^26 + (b >> 6)
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
@@ -334,6 +335,113 @@ __global__ void __launch_bounds__(256) k_reference_layer(LayerParams P) {
             P.rgba[p0 + k] = px[k];
         }
     composite4(P, p0, count, px);
+}
+
+// ---- moveref fast path --------------------------------------------------------------------------
+// The configuration every README example and the benchmark use: one source, default movement flags,
+// no masks except the reset mask, reset off or random with device draws, single fused layer.  All
+// configuration branches are compile-time, the random test runs in fp32 with an exact fallback, and a
+// thread's four pixels move as 128-bit words end to end.
+struct FastParams {
+    const float2* flow;
+    const int4* old;
+    int4* out;
+    uchar4* rgba;
+    const float* reset_scale;
+    float reset_factor;
+    const uint8_t* pix;
+    uint8_t* rgb;
+    uint32_t bg;
+    int h, w, n;
+    uint64_t seed, frame;
+    int* err;
+};
+
+template <int RESET, int CHAN>
+__global__ void __launch_bounds__(256) k_moveref_fast(FastParams P) {
+    const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (p0 >= P.n) return;
+    float2 f[4];
+    {
+        float4 a = __ldg(reinterpret_cast<const float4*>(P.flow + p0));
+        float4 b = __ldg(reinterpret_cast<const float4*>(P.flow + p0) + 1);
+        f[0] = make_float2(a.x, a.y); f[1] = make_float2(a.z, a.w);
+        f[2] = make_float2(b.x, b.y); f[3] = make_float2(b.z, b.w);
+    }
+    int q[4];
+    bool moved[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int off = __float2int_rn(f[k].y) * P.w + __float2int_rn(f[k].x);
+        moved[k] = off != 0;
+        q[k] = moved[k] ? wrap_index(p0 + k + off, P.n, p0 + k, P.err) : p0 + k;
+    }
+    int4 rec[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) rec[k] = __ldg(P.old + q[k]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        // a transparent source does not move (movement.py:34-35): keep the pixel's own record
+        if (moved[k] && rec[k].z == 0) rec[k] = __ldg(P.old + p0 + k);
+        else if (moved[k]) rec[k].z = 1;
+    }
+    if (RESET == TF_RESET_RANDOM) {
+        int y = p0 / P.w, x = p0 - y * P.w;
+        float4 thr4 = P.reset_scale ? __ldg(reinterpret_cast<const float4*>(P.reset_scale + p0))
+                                    : make_float4(P.reset_factor, P.reset_factor, P.reset_factor, P.reset_factor);
+        const float thr[4] = {thr4.x, thr4.y, thr4.z, thr4.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint4 r = philox4x32_7(P.seed, P.frame, (uint32_t)(p0 + k) >> 1);
+            uint32_t a = (k & 1) ? r.z : r.x, b = (k & 1) ? r.w : r.y;
+            // r = ((a >> 5) * 2^26 + (b >> 6)) / 2^53 lies in [lo, lo + 2^-23): decide in fp32, exact otherwise
+            float lo = __uint_as_float(0x3f800000u | (a >> 9)) - 1.0f;
+            bool hit;
+            if (lo + 1.1920929e-07f <= thr[k]) hit = true;
+            else if (lo >= thr[k]) hit = false;
+            else hit = ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0) < (double)thr[k];
+            if (hit) {
+                rec[k].x = y;
+                rec[k].y = x;
+                rec[k].z = 1;
+            }
+            if (++x == P.w) {
+                x = 0;
+                y++;
+            }
+        }
+    }
+    uchar4 px[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        bool sel = rec[k].w == 0 && rec[k].z != 0;
+        if (sel) {
+            size_t at = (size_t)clampi(rec[k].x, 0, P.h - 1) * P.w + clampi(rec[k].y, 0, P.w - 1);
+            if (CHAN == 4) {
+                px[k] = __ldg(reinterpret_cast<const uchar4*>(P.pix) + at);
+            } else {
+                const uint8_t* src = P.pix + at * 3;
+                px[k] = make_uchar4(__ldg(src), __ldg(src + 1), __ldg(src + 2), 1);
+            }
+        } else {
+            px[k] = P.rgba[p0 + k];      // keeps the stale colour (quirk Q10); RGB sources clear the alpha
+            if (CHAN == 3) px[k].w = 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) P.out[p0 + k] = rec[k];
+    *reinterpret_cast<uint4*>(P.rgba + p0) = make_uint4(*reinterpret_cast<uint32_t*>(&px[0]), *reinterpret_cast<uint32_t*>(&px[1]),
+                                                        *reinterpret_cast<uint32_t*>(&px[2]), *reinterpret_cast<uint32_t*>(&px[3]));
+    // composite over the constant background, 12 packed bytes
+    uint32_t c[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        c[k] = px[k].w != 0 ? ((uint32_t)px[k].x | ((uint32_t)px[k].y << 8) | ((uint32_t)px[k].z << 16))
+                            : (((P.bg >> 16) & 255u) | (P.bg & 0xff00u) | ((P.bg & 255u) << 16));
+    uint32_t* wp = reinterpret_cast<uint32_t*>(P.rgb + (size_t)p0 * 3);
+    wp[0] = c[0] | (c[1] << 24);
+    wp[1] = (c[1] >> 8) | (c[2] << 16);
+    wp[2] = (c[2] >> 16) | (c[3] << 8);
 }
 
 // ---- static (static.py:13-17) -----------------------------------------------------------------
@@ -666,9 +774,30 @@ extern "C" int tf_layer_update(tf_layer* l, const float* flow, const tf_pixmap* 
                 k_mark_vacated<0><<<blocks1, 256, 0, st>>>(P, 1);
                 TF_LAUNCHED();
             }
+            const tf_layer_config& c = l->cfg;
+            bool fast = n_pixmaps == 1 && !leave && !c.transparent_pixels_can_move && c.pixels_can_move_to_empty_spot &&
+                        c.pixels_can_move_to_filled_spot && !l->mask_src && !l->mask_dst && !l->mask_alpha &&
+                        (c.reset_mode == TF_RESET_OFF || (c.reset_mode == TF_RESET_RANDOM && !random && !c.reset_source)) &&
+                        rgb_inout && first_layer && (P.n & 3) == 0 && ((uintptr_t)flow & 15) == 0 &&
+                        ((uintptr_t)l->reset_scale & 15) == 0;
             {
                 ScopedKernelTimer timer(TFK_COMPOSITOR_LAYER, st);
-                k_reference_layer<TF_LAYER_MOVEREF><<<blocks4, 256, 0, st>>>(P);
+                if (fast) {
+                    FastParams F;
+                    F.flow = P.flow; F.old = P.old; F.out = P.out; F.rgba = P.rgba; F.reset_scale = l->reset_scale;
+                    F.reset_factor = c.reset_random_factor; F.pix = P.pix[0]; F.rgb = rgb_inout; F.bg = background_rgb;
+                    F.h = P.h; F.w = P.w; F.n = P.n; F.seed = P.seed; F.frame = P.frame; F.err = P.err;
+                    bool rnd = c.reset_mode == TF_RESET_RANDOM;
+                    if (P.chan[0] == 4) {
+                        if (rnd) k_moveref_fast<TF_RESET_RANDOM, 4><<<blocks4, 256, 0, st>>>(F);
+                        else k_moveref_fast<TF_RESET_OFF, 4><<<blocks4, 256, 0, st>>>(F);
+                    } else {
+                        if (rnd) k_moveref_fast<TF_RESET_RANDOM, 3><<<blocks4, 256, 0, st>>>(F);
+                        else k_moveref_fast<TF_RESET_OFF, 3><<<blocks4, 256, 0, st>>>(F);
+                    }
+                } else {
+                    k_reference_layer<TF_LAYER_MOVEREF><<<blocks4, 256, 0, st>>>(P);
+                }
             }
             TF_LAUNCHED();
             l->cur ^= 1;
