@@ -287,8 +287,11 @@ def run_ours(args):
     if dom:
         tot_ms, n = cand[dom]
         achieved = alg[dom] / (tot_ms / n / 1000.0) / 1e9
+        # DRAM traffic of the same kernel from the committed ncu --set full capture
+        # (profiles/r01_ncu_full_k_fb_iter_tile.txt: 428.36 MB read + 58.62 MB written per 4K launch)
+        traffic = 486.99e6 if (dom == "fb_iter_finest" and (H, W) == (H4K, W4K)) else None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "avg_launch_ms": tot_ms / n, "launches": n, "share_of_step": tot_ms / ms,
                     "algorithmic_bytes_per_launch": alg[dom]}
     frame_bytes = fb.algorithmic_bytes(True) + (24.0 + 50.0) * n_px + 3.0 * n_px + n_px
@@ -389,8 +392,8 @@ def run_e2e(args, clip, pixmap, layer_cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--height", type=int, default=H4K)
     ap.add_argument("--width", type=int, default=W4K)
