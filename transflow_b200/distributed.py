@@ -56,9 +56,10 @@ class ShardedFlowStream:
     """
 
     def __init__(self, rank, world, chunk_pairs, counts, estimate_chunk, accumulate, flow_shape, device,
-                 group=None, transport="nccl"):
+                 group=None, transport="nccl", round_hook=None):
         self.rank, self.world, self.k = rank, world, chunk_pairs
         self.transport = transport
+        self.round_hook = round_hook      # called on every rank with the round index before the round starts
         self.counts = list(counts)
         self.owners = round_slots(self.counts)
         self.cpr = len(self.owners)
@@ -100,6 +101,8 @@ class ShardedFlowStream:
         ring = self.ring
         for j in range(first_round, first_round + n_rounds):
             base_chunk = j * self.cpr
+            if self.round_hook is not None:
+                self.round_hook(j)
             if self.rank == 0:
                 index = [0] * self.world              # next ring slot per producer in this round
                 for slot, owner in enumerate(self.owners):
@@ -136,6 +139,8 @@ class ShardedFlowStream:
         if self.rank == 0:
             pending = self._post_receives(first_round)
             for j in range(first_round, last + 1):
+                if self.round_hook is not None:
+                    self.round_hook(j)
                 upcoming = self._post_receives(j + 1) if j < last else {}
                 base_chunk = j * self.cpr
                 for slot, owner in enumerate(self.owners):
@@ -152,6 +157,8 @@ class ShardedFlowStream:
         else:
             in_flight = []       # (works, tensors) of the previous round: bounded look-ahead
             for j in range(first_round, last + 1):
+                if self.round_hook is not None:
+                    self.round_hook(j)
                 base_chunk = j * self.cpr
                 works, keep = [], []
                 for slot, owner in enumerate(self.owners):
@@ -254,12 +261,24 @@ def bench_sharded(args, rank, world, local):
         copied = [None, None]
         count = {"n": 0}
 
+    fanout_box = {"f": None, "frames": 0}
+
     def accumulate(flow):
         k = count["n"] & 1
         count["n"] += 1
         if io["host"] and copied[k] is not None:
             torch.cuda.current_stream().wait_event(copied[k])   # the D2H out of this buffer is done
         comp.step(flow, rgb[k])
+        fan = fanout_box["f"]
+        if io["host"] and fan is not None:
+            target = fanout_box["frames"] % world            # frame i leaves through rank i % N's PCIe link
+            fanout_box["frames"] += 1
+            if target != 0:
+                fan.send(rgb[k], target)
+                done = torch.cuda.Event()
+                done.record()
+                copied[k] = done                              # rgb[k] may be rewritten once the peer copy ran
+                return
         if io["host"]:
             ready = torch.cuda.Event()
             ready.record()
@@ -292,8 +311,23 @@ def bench_sharded(args, rank, world, local):
     f_ms, a_ms = float(plan[0]), float(plan[1])
     counts = plan_round(world, Q, f_ms, a_ms)
     transport = os.environ.get("TFB200_TRANSPORT", "p2p")
+    frames_per_round = sum(counts) * K
+    fan = None
+    if os.environ.get("TFB200_FANOUT", "1") == "1":
+        from .peer import PeerFrameFanout
+        fan = PeerFrameFanout(rank, world, (H, W, 3))
+        fanout_box["f"] = fan
+    e2e_first_round = {"j": None}
+
+    def round_hook(j):
+        # in the end-to-end pass, every non-zero rank queues the D2H of the frames it will be handed
+        if io["host"] and fan is not None and rank != 0:
+            if e2e_first_round["j"] is None:
+                e2e_first_round["j"] = j
+            lo = (j - e2e_first_round["j"]) * frames_per_round
+            fan.expect(sum(1 for i in range(lo, lo + frames_per_round) if i % world == rank))
     stream = ShardedFlowStream(rank, world, K, counts, estimate_chunk, accumulate, (H, W, 2), "cuda",
-                               transport=transport)
+                               transport=transport, round_hook=round_hook)
 
     def timed_rounds(first):
         stream.run(first, args.warmup)
@@ -345,7 +379,9 @@ def bench_sharded(args, rank, world, local):
             "e2e": {"value": frames / (float(ms_e2e) / 1000.0), "unit": "frames/s",
                     "h2d_bytes_per_step": int(stream.frames_per_round * n_px * 3 * (K + 1) / K),
                     "d2h_bytes_per_step": int(stream.frames_per_round * n_px * 3),
-                    "api": "sharded stream: pinned BGR frames H2D on every rank, RGB frames D2H on rank 0"},
+                    "api": "sharded stream: pinned BGR frames H2D on every rank; RGB frame i leaves through rank i % N's "
+                           "PCIe link (rank 0 hands it over NVLink)" if fan is not None else
+                           "sharded stream: pinned BGR frames H2D on every rank, RGB frames D2H on rank 0"},
             "gpu_launches": int(launches), "clocks": clocks,
             "pipeline_hbm_frac": frame_bytes * fps / 1e9 / (peak * world),
             "exchange_bytes_per_step": int(sum(counts[1:]) * K * n_px * 8),

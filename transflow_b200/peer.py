@@ -119,3 +119,69 @@ class PeerFlowRing:
 
     def release(self, producer: int, round_index: int):
         flag_signal(self.consumed_peer[producer], round_index + 1)
+
+
+class PeerFrameFanout:
+    """Spreads rank 0's finished RGB frames over every rank's PCIe link.
+
+    The accumulate+remap recurrence runs on rank 0 only, so at N GPUs its single PCIe link would
+    have to carry every output frame (25 MB at 4K).  Instead rank 0 stores frame i into the output
+    ring of rank i % N over NVLink (a kernel doing 128-bit peer stores, then a release flag), and
+    that rank's copy stream -- waiting on the flag with a stream memory op -- moves it to its own
+    pinned host buffer.  Per-slot ``freed`` counters flow back the same way.
+    """
+
+    def __init__(self, rank: int, world: int, frame_shape, slots: int = 4, group=None):
+        self.rank, self.world, self.slots = rank, world, slots
+        self.frame_shape = tuple(frame_shape)
+        self.frame_bytes = 1
+        for s in self.frame_shape:
+            self.frame_bytes *= int(s)
+        self.frame_bytes_padded = (self.frame_bytes + 255) // 256 * 256
+        self.lib = _lib.load()
+        mine = {}
+        if rank == 0:
+            self.freed = {r: DeviceBuffer(256) for r in range(1, world)}
+            for r, buf in self.freed.items():
+                mine[f"freed{r}"] = buf.handle()
+            self.sent = [0] * world
+        else:
+            self.ring = DeviceBuffer(slots * self.frame_bytes_padded)
+            self.filled = DeviceBuffer(256)
+            mine["ring"] = self.ring.handle()
+            mine["filled"] = self.filled.handle()
+            self.received = 0
+            self.stream = torch.cuda.Stream()
+            self.host = [torch.empty(self.frame_shape, dtype=torch.uint8).pin_memory() for _ in range(slots)]
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine, group=group)
+        if rank == 0:
+            self.ring_peer = {r: open_ipc(everyone[r]["ring"]) for r in range(1, world)}
+            self.filled_peer = {r: open_ipc(everyone[r]["filled"]) for r in range(1, world)}
+        else:
+            self.freed_peer = open_ipc(everyone[0][f"freed{rank}"])
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+    # rank 0, on the compute stream, right after the frame was produced ----------------------------
+    def send(self, frame: torch.Tensor, target: int):
+        seq = self.sent[target] + 1
+        slot = (seq - 1) % self.slots
+        if seq > self.slots:
+            flag_wait_geq(self.freed[target].address, seq - self.slots)
+        dst = self.ring_peer[target] + slot * self.frame_bytes_padded
+        check(self.lib.tf_copy_to_peer(C.c_void_p(dst), C.c_void_p(frame.data_ptr()), self.frame_bytes, stream_ptr()))
+        flag_signal(self.filled_peer[target], seq)
+        self.sent[target] = seq
+
+    # receiving rank: enqueue the wait + D2H + release for the next n frames (does not block the host) ----
+    def expect(self, n: int):
+        with torch.cuda.stream(self.stream):
+            for _ in range(n):
+                seq = self.received + 1
+                slot = (seq - 1) % self.slots
+                flag_wait_geq(self.filled.address, seq)
+                src = self.ring.tensor(slot * self.frame_bytes_padded, self.frame_shape, torch.uint8)
+                self.host[slot].copy_(src, non_blocking=True)
+                flag_signal(self.freed_peer, seq)
+                self.received = seq
