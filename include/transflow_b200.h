@@ -76,7 +76,8 @@ TF_API int tf_farneback_destroy(tf_farneback* h);
  * since a frame is the right image of one pair and the left image of the next). */
 TF_API int tf_farneback_prepare(tf_farneback* h, int slot, const uint8_t* gray, void* stream);
 /* Coarse-to-fine displacement solve between two prepared slots -> flow (H, W, 2).
- * variant: 3 = fused rolling-tile iteration kernel (default); 1 = unfused reference kernels
+ * variant: 4-7 = fused half-buffer iteration kernel (fb_half.cuh; scalar or 128-bit shared accesses, 4 or 3
+ * CTAs per SM); 3 = fused rolling-tile iteration kernel (default); 1 = unfused reference kernels
  * (M and double vertical sums materialised in HBM); 0 / 2 = fused column-streaming kernel with
  * float / double sums in shared memory (kept for comparison).
  * If clip != 0 the final clip of FlowSource.post_process (source.py:361-362) is fused into
@@ -100,6 +101,8 @@ TF_API int tf_farneback_level_size(const tf_farneback* h, int level_index, int* 
  * level during the last solve.  level_index 0 = coarsest. */
 TF_API int tf_farneback_debug_read(tf_farneback* h, int slot, int level_index, int what, float* out,
                             void* stream);
+/* Tuning knob for experiments (process-wide): key 0 = rows per CTA of the variant 4-6 kernels (0 = heuristic). */
+TF_API int tf_farneback_tune(int key, int value);
 /* Algorithmic bytes moved per solved pair (SURVEY.md 8d model), for roofline reporting. */
 TF_API double tf_farneback_algorithmic_bytes(const tf_farneback* h, int reuse_r);
 

@@ -187,7 +187,7 @@ def test_farneback_stages_match_restatement(params):
         assert np.abs(R - wantR).max() < 2e-4, (li, np.abs(R - wantR).max())
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 6])
 @pytest.mark.parametrize("params", FB_PARAMS)
 @pytest.mark.parametrize("shape", [(135, 201), (480, 854)])
 def test_farneback_matches_cv2(shape, params, variant):

@@ -10,6 +10,8 @@ h, w = int(os.environ.get("PROF_H", 2160)), int(os.environ.get("PROF_W", 3840))
 clip = synthetic_clip(h, w, 2, seed=1)
 a, b = (torch.from_numpy(F.gray_from_bgr(f)).cuda() for f in clip)
 fb = ops.Farneback(h, w)
+if os.environ.get("PROF_ROWS"):
+    fb.lib.tf_farneback_tune(0, int(os.environ["PROF_ROWS"]))
 out = torch.empty((h, w, 2), dtype=torch.float32, device="cuda")
 for _ in range(int(os.environ.get("PROF_REPS", 3))):
     fb.prepare(0, a); fb.prepare(1, b); fb.solve(0, 1, out)

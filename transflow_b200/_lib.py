@@ -74,6 +74,7 @@ SIGNATURES = {
     "tf_farneback_level_size": (_i, [_vp, _i, _pi, _pi]),
     "tf_farneback_debug_read": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "tf_farneback_algorithmic_bytes": (_d, [_vp, _i]),
+    "tf_farneback_tune": (_i, [_i, _i]),
     "tf_hs_create": (_i, [C.POINTER(_vp), _i, _i]),
     "tf_hs_destroy": (_i, [_vp]),
     "tf_hs_run": (_i, [_vp, _vp, _vp, _vp, _d, _i, _d, _d, _vp, _i, _pi, _vp]),

@@ -466,6 +466,14 @@ __global__ void __launch_bounds__(256) k_fb_box_h_solve(const double* __restrict
 
 #include "fb_iter.cuh"
 #include "fb_tile.cuh"
+#include "fb_half.cuh"
+
+int g_fbh_rows = 0;
+extern "C" int tf_farneback_tune(int key, int value) {
+    if (key == 0) g_fbh_rows = value;
+    else return fail(TF_ERR_INVALID_ARG, "tf_farneback_tune: unknown key %d", key);
+    return TF_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // C ABI
@@ -679,6 +687,10 @@ static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int var
         } else if (variant == 3) {
             if (int e = fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st))
                 return e;
+        } else if (variant >= 4) {
+            if (int e = fb_iterate_half<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest,
+                                            variant, st))
+                return e;
         } else {
             if (int e = fb_iterate_fused<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest,
                                              variant == 2, finest, st))
@@ -694,7 +706,7 @@ extern "C" int tf_farneback_solve(tf_farneback* h, int slot_left, int slot_right
     TF_REQUIRE(h && flow, TF_ERR_INVALID_ARG, "tf_farneback_solve: null argument");
     TF_REQUIRE((slot_left == 0 || slot_left == 1) && (slot_right == 0 || slot_right == 1), TF_ERR_INVALID_ARG,
                "tf_farneback_solve: slots must be 0 or 1");
-    TF_REQUIRE(variant >= 0 && variant <= 3, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
+    TF_REQUIRE(variant >= 0 && variant <= 7, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
     TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_solve: flow must be 8-byte aligned");
     cudaStream_t st = as_stream(stream);
     float2* out = reinterpret_cast<float2*>(flow);
@@ -708,7 +720,7 @@ extern "C" int tf_farneback_step(tf_farneback* h, int new_slot, const uint8_t* g
     TF_REQUIRE((new_slot == 0 || new_slot == 1) && (slot_left == 0 || slot_left == 1) &&
                    (slot_right == 0 || slot_right == 1),
                TF_ERR_INVALID_ARG, "tf_farneback_step: slots must be 0 or 1");
-    TF_REQUIRE(variant >= 0 && variant <= 3, TF_ERR_INVALID_ARG, "tf_farneback_step: unknown variant %d", variant);
+    TF_REQUIRE(variant >= 0 && variant <= 7, TF_ERR_INVALID_ARG, "tf_farneback_step: unknown variant %d", variant);
     TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_step: flow must be 8-byte aligned");
     cudaStream_t st = as_stream(stream);
     if (!h->aux) {
