@@ -101,7 +101,8 @@ TF_API int tf_farneback_level_size(const tf_farneback* h, int level_index, int* 
  * level during the last solve.  level_index 0 = coarsest. */
 TF_API int tf_farneback_debug_read(tf_farneback* h, int slot, int level_index, int what, float* out,
                             void* stream);
-/* Tuning knob for experiments (process-wide): key 0 = rows per CTA of the variant 4-6 kernels (0 = heuristic). */
+/* Tuning knob for experiments (process-wide): key 0 = rows per CTA of the variant 4-7 kernels (0 = heuristic);
+ * key 1 = 1 selects the separate horizontal / vertical pyramid blur passes instead of the fused kernel. */
 TF_API int tf_farneback_tune(int key, int value);
 /* Algorithmic bytes moved per solved pair (SURVEY.md 8d model), for roofline reporting. */
 TF_API double tf_farneback_algorithmic_bytes(const tf_farneback* h, int reuse_r);
@@ -137,6 +138,30 @@ TF_API int tf_flow_postprocess(float* flow, const float* mask, int forward, int3
  * out == NULL or out == flow -> in place. */
 TF_API int tf_flow_postprocess_to(float* flow, const float* mask, int forward, int32_t* owner, float* out,
                                   int height, int width, void* stream);
+
+/* ---- flow filters, mask, convolution kernel: transflow/flow/filters.py:36-68, source.py:339-348 ---------- */
+enum { TF_FLOW_SCALE = 0, TF_FLOW_THRESHOLD = 1, TF_FLOW_CLIP = 2 };
+#define TF_MAX_FLOW_OPS 8
+/* One elementwise filter with its per-frame scalar (the reference evaluates a lambda of t).  strong != 0:
+ * the scalar is a NumPy float64 (comparisons / products in float64, rounded to float32); strong == 0: a Python
+ * number, which NumPy treats as float32 next to the float32 flow. */
+typedef struct tf_flow_op {
+    int kind;
+    int strong;
+    double value;
+} tf_flow_op;
+/* post_process with the filters fused in front of the mask multiply (everything in one pass over the flow).
+ * ops is a HOST array (copied into the launch).  out == NULL -> in place. */
+TF_API int tf_flow_postprocess_ex(float* flow, const tf_flow_op* ops, int n_ops, const float* mask, int forward,
+                                  int32_t* owner, float* out, int height, int width, void* stream);
+/* filters + mask only -> out (the stage in front of the convolution kernel). */
+TF_API int tf_flow_filters(const float* flow, const tf_flow_op* ops, int n_ops, const float* mask, float* out,
+                           int height, int width, void* stream);
+/* scipy.signal.convolve2d(mode="same", boundary="fill") of both flow channels with a float64 kernel (kh, kw)
+ * in DEVICE memory; float64 accumulation, float32 result.  forward != 0: the float32 value is chosen so that the
+ * round-half-even of the forward conversion equals the float64 one.  Not in place. */
+TF_API int tf_flow_convolve(const float* flow, const double* kernel, int kh, int kw, int forward, float* out,
+                            int height, int width, void* stream);
 
 /* ---- compositor: transflow/compositor/** ---------------------------------------------------- */
 enum { TF_LAYER_MOVEREF = 0, TF_LAYER_SUM = 1, TF_LAYER_STATIC = 2, TF_LAYER_INTRODUCTION = 3 };

@@ -118,16 +118,51 @@ def horn_schunck(left, right, flow=None, alpha=1, max_iters=3, decay=0, delta=1,
     return np.stack([u, v], axis=-1).astype(np.float32)
 
 
-def post_process(flow: np.ndarray, forward: bool, mask=None) -> np.ndarray:
-    """``FlowSource.post_process`` (``flow/sources/source.py:337-363``) without filters/kernel.
+def apply_filter(flow: np.ndarray, name: str, value, t: float = 0.0) -> None:
+    """One flow filter, in place (``flow/filters.py:36-87``).  ``value`` is the per-frame scalar the
+    reference gets from ``expr(t)`` (for ``polar``: a pair of callables of ``(t, r, a)``)."""
+    h, w, _ = flow.shape
+    if name == "scale":                                   # filters.py:41
+        flow *= value
+        return
+    norm = np.linalg.norm(flow.reshape(h * w, 2), axis=1).reshape((h, w))
+    if name == "threshold":                               # filters.py:49-53
+        flow[np.where(norm <= value)] = 0
+    elif name == "clip":                                  # filters.py:61-68
+        factors = np.ones((h, w))
+        where = np.where(norm >= value)
+        factors[where] = value / norm[where]
+        flow[:, :, 0] *= factors
+        flow[:, :, 1] *= factors
+    elif name == "polar":                                 # filters.py:80-86
+        theta = np.atan2(flow[:, :, 1], flow[:, :, 0])
+        new_radius = value[0](t, norm, theta)
+        new_theta = value[1](t, norm, theta)
+        flow[:, :, 1] = new_radius * np.sin(new_theta)
+        flow[:, :, 0] = new_radius * np.cos(new_theta)
+    else:
+        raise ValueError(f"Unknown filter name '{name}'")
 
+
+def post_process(flow: np.ndarray, forward: bool, mask=None, kernel=None, filters=(), t: float = 0.0) -> np.ndarray:
+    """``FlowSource.post_process`` (``flow/sources/source.py:337-363``).
+
+    filters ([(name, scalar), ...], source.py:339-341) -> mask (:342-343) -> convolution kernel through the
+    reference's own ``scipy.signal.convolve2d`` call (:344-348; the flow is float64 from there on) ->
     forward: clip, half-even round, scatter source coordinates to their targets (last writer
     in raster order wins), flow := origin - target; then the final clip (always).  Mutates
-    ``flow`` in place like the reference unless a mask forces a copy.
+    ``flow`` in place like the reference unless a mask / kernel forces a copy.
     """
+    for name, value in filters:
+        apply_filter(flow, name, value, t)
     h, w = flow.shape[:2]
     if mask is not None:
         flow = np.multiply(np.asarray(mask, np.float32).reshape(h, w, 1), flow)
+    if kernel is not None:
+        import scipy.signal
+        fx = scipy.signal.convolve2d(flow[:, :, 0], kernel, mode="same", boundary="fill", fillvalue=0)
+        fy = scipy.signal.convolve2d(flow[:, :, 1], kernel, mode="same", boundary="fill", fillvalue=0)
+        flow = np.stack([fx, fy], axis=-1)
     xs = np.arange(w, dtype=np.int32)[None, :]
     ys = np.arange(h, dtype=np.int32)[:, None]
     lo_x, hi_x, lo_y, hi_y = -xs, w - 1 - xs, -ys, h - 1 - ys

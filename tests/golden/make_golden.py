@@ -230,11 +230,74 @@ def kat_cases():
     np.savez_compressed(os.path.join(HERE, "kat_golden.npz"), **out)
 
 
+def postprocess_cases(tmp):
+    """Reference ``FlowSource.post_process`` with flow filters, a mask and a convolution kernel
+    (``flow/filters.py``, ``flow/sources/source.py:337-363``), driven through ``FlowSource.from_args`` on the
+    same FFV1 clip as ``flow_cases`` (the raw flow is cv2 Farneback with the default parameters)."""
+    import cv2
+    import json
+    from transflow.flow.sources.source import FlowSource
+    from transflow_b200.synthetic import synthetic_clip
+
+    fh, fw, n = 96, 128, 4
+    clip = synthetic_clip(fh, fw, n, seed=3)
+    avi = os.path.join(tmp, "clip_pp.avi")
+    vw = cv2.VideoWriter(avi, cv2.VideoWriter_fourcc(*"FFV1"), 25, (fw, fh))
+    for f in clip:
+        vw.write(f)
+    vw.release()
+    cfg_path = os.path.join(tmp, "fb.json")
+    with open(cfg_path, "w") as fp:
+        json.dump(dict(method="farneback"), fp)
+    rng = np.random.default_rng(11)
+    grad = np.clip(np.add.outer(np.linspace(0, 200, fh), np.linspace(0, 55, fw)), 0, 255).astype(np.uint8)
+    p_mask = os.path.join(tmp, "pp_mask.png")
+    save_mask_png(grad, p_mask)
+    kernels = {"box3": np.full((3, 3), 1 / 9), "rand45": rng.normal(size=(4, 5)), "row7": rng.normal(size=(1, 7)) * 0.5}
+    kpaths = {}
+    for kname, k in kernels.items():
+        kpaths[kname] = os.path.join(tmp, kname + ".npy")
+        np.save(kpaths[kname], k)
+    cases = {
+        "scale": dict(flow_filters="scale=2+t", direction="backward"),
+        "threshold_fw": dict(flow_filters="threshold=0.5", direction="forward"),
+        "clip": dict(flow_filters="clip=1.5*(1+t)", direction="backward"),
+        "chain_mask_fw": dict(flow_filters="scale=0.5;clip=1;threshold=0.2", mask_path=p_mask, direction="forward"),
+        "strong": dict(flow_filters="scale=numpy.float64(1.5)+t;clip=numpy.sqrt(2.0);threshold=numpy.float64(0.3)",
+                       direction="backward"),
+        "polar": dict(flow_filters="polar=r*2:a+t", direction="backward"),
+        "polar_mid": dict(flow_filters="scale=3;polar=r+1:-a;clip=2", direction="forward"),
+        "kernel_box3": dict(kernel_path=kpaths["box3"], direction="backward"),
+        "kernel_box3_fw": dict(kernel_path=kpaths["box3"], direction="forward"),
+        "kernel_rand45_mask_fw": dict(kernel_path=kpaths["rand45"], mask_path=p_mask, flow_filters="scale=4",
+                                      direction="forward"),
+        "kernel_row7": dict(kernel_path=kpaths["row7"], flow_filters="clip=2", direction="backward"),
+    }
+    from transflow.utils import load_float_mask
+    out = {"clip": clip, "mask": load_float_mask(p_mask), "framerate": np.array(25.0)}
+    for kname, k in kernels.items():
+        out["kernel/" + kname] = k
+    for name, kw in cases.items():
+        with FlowSource.from_args(avi, cv_config=cfg_path, **kw) as src:
+            flows = np.stack([np.array(f) for f in src])
+        assert flows.shape == (n - 1, fh, fw, 2)
+        out[f"{name}/flows"] = flows          # float32, float64 after a convolution kernel
+        out[f"{name}/args"] = np.array(json.dumps({k: (os.path.basename(v) if k.endswith("_path") else v)
+                                                   for k, v in kw.items()}))
+    np.savez_compressed(os.path.join(HERE, "postprocess_golden.npz"), **out)
+    print("post-process cases:", len(cases))
+
+
 if __name__ == "__main__":
+    only = sys.argv[1:]
     with tempfile.TemporaryDirectory() as tmp:
-        compositor_cases(tmp)
-        kat_cases()
-        flow_cases(tmp)
+        if not only or "compositor" in only:
+            compositor_cases(tmp)
+            kat_cases()
+        if not only or "flow" in only:
+            flow_cases(tmp)
+        if not only or "postprocess" in only:
+            postprocess_cases(tmp)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

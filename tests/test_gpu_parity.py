@@ -187,6 +187,26 @@ def test_farneback_stages_match_restatement(params):
         assert np.abs(R - wantR).max() < 2e-4, (li, np.abs(R - wantR).max())
 
 
+@pytest.mark.parametrize("shape,params", [((135, 201), dict()), ((270, 484), dict(pyr_scale=0.7, levels=4)),
+                                          ((1080, 1920), dict()), ((480, 854), dict(pyr_scale=0.35, levels=3))])
+def test_farneback_fused_pyramid_is_bit_identical_to_two_pass(shape, params):
+    """The fused blur+resize kernel keeps the operation order of the separate passes."""
+    from transflow_b200 import ops, _lib
+    h, w = shape
+    g0, _ = clip_pair(h, w, seed=5)
+    fb = ops.Farneback(h, w, **params)
+    lib = _lib.load()
+    try:
+        lib.tf_farneback_tune(1, 1)
+        fb.prepare(0, dev(g0))
+        want = [fb.debug_read(0, li, 0).cpu().numpy() for li in range(len(fb.level_sizes))]
+    finally:
+        lib.tf_farneback_tune(1, 0)
+    fb.prepare(0, dev(g0))
+    for li, ref in enumerate(want):
+        np.testing.assert_array_equal(fb.debug_read(0, li, 0).cpu().numpy(), ref)
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 6])
 @pytest.mark.parametrize("params", FB_PARAMS)
 @pytest.mark.parametrize("shape", [(135, 201), (480, 854)])
@@ -305,6 +325,82 @@ def test_lucas_kanade_golden_flow_source():
             got = pp(lk(grays[t], grays[t - 1])).cpu().numpy()     # backward: (cur, prev)
             mean, mx = epe(got, z[f"{name}/backward"][t - 1])
             assert mean <= 0.01 and mx <= 0.1, (name, t, mean, mx)
+
+
+# ------------------------------------------------------------------------------------------------
+# flow filters + mask + convolution kernel against what the reference produced
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", G.POSTPROCESS_CASES)
+def test_postprocess_filters_mask_kernel_match_reference(name):
+    """Same raw flow as the reference (cv2 Farneback on the golden clip) through the device post-process:
+    scalar filters, mask and the forward scatter are bit-exact; the float64 convolution is rounded to the
+    float32 flow type (<= 1 ulp; exact integers in the forward direction); ``polar`` is transcendental."""
+    import torch
+    from transflow_b200 import ops
+    from transflow_b200.flow.filters import FlowFilter
+    z = G.load("postprocess_golden.npz")
+    direction, filters, mask, kernel = G.postprocess_case_inputs(z, name)
+    flts = [FlowFilter.from_args(k, (e,) if isinstance(e, str) else tuple(e)) for k, e in filters]
+    grays = [F.gray_from_bgr(f) for f in z["clip"]]
+    h, w = grays[0].shape
+    post = ops.PostProcess(h, w, direction == "forward", mask=None if mask is None else dev(mask), kernel=kernel)
+    want = z[f"{name}/flows"]
+    for i in range(1, len(grays)):
+        left, right = (grays[i - 1], grays[i]) if direction == "forward" else (grays[i], grays[i - 1])
+        t = i / float(z["framerate"])
+        flow = dev(F.farneback(left, right))
+        pending = []
+        for flt in flts:            # FlowSource.post_process: scalar runs are fused, polar splits them
+            if flt.kind is not None:
+                pending.append(flt.op(t))
+                continue
+            for op in pending:
+                arr, n = ops._pack_flow_ops([op])
+                ops.check(post.lib.tf_flow_filters(ops.ptr(flow), arr, n, None, ops.ptr(flow), h, w, ops.stream_ptr()))
+            pending = []
+            flt.apply(flow, t)
+        got = post(flow, ops=pending).cpu().numpy()
+        ref = want[i - 1].astype(np.float32)
+        if any(k == "polar" for k, _ in filters):
+            if direction == "forward":
+                assert (np.abs(got - ref).max(axis=-1) > 0).mean() < 2e-3
+            else:
+                np.testing.assert_allclose(got, ref, atol=2e-5)
+        elif kernel is not None:
+            assert (got != ref).mean() < 1e-3, (got != ref).mean()
+            np.testing.assert_allclose(got, ref, rtol=2e-7, atol=1e-30 if direction == "backward" else 2.0)
+        else:
+            np.testing.assert_array_equal(got, ref)
+
+
+@pytest.mark.parametrize("name", ["chain_mask_fw", "strong", "kernel_row7", "polar"])
+def test_flow_source_plugin_with_filters(name, tmp_path):
+    """The whole plugin path (device Farneback + fused post-process) given the reference's arguments."""
+    import json
+    import PIL.Image
+    from transflow_b200.flow import FlowSource
+    from transflow_b200.flow.sources.cv import ArrayCapture
+    z = G.load("postprocess_golden.npz")
+    args = json.loads(str(z[f"{name}/args"]))
+    if args.get("mask_path"):
+        path = str(tmp_path / "mask.png")
+        PIL.Image.fromarray(np.rint(z["mask"] * 255).astype(np.uint8)).save(path)
+        args["mask_path"] = path
+    if args.get("kernel_path"):
+        path = str(tmp_path / "kernel.npy")
+        np.save(path, z["kernel/" + args["kernel_path"][:-4]])
+        args["kernel_path"] = path
+    with FlowSource.from_args(ArrayCapture(z["clip"], 25.0), **args) as src:
+        flows = list(src)
+    want = z[f"{name}/flows"]
+    assert len(flows) == len(want)
+    for got, ref in zip(flows, want):
+        assert got.dtype == np.float32
+        if args["direction"] == "backward":
+            mean, mx = epe(got, ref.astype(np.float32))
+            assert mean <= 0.01 and mx <= 0.1, (name, mean, mx)
+        else:
+            assert (np.abs(got - ref).max(axis=-1) > 0).mean() < 5e-3
 
 
 # ------------------------------------------------------------------------------------------------

@@ -125,6 +125,36 @@ def test_flow_oracle_matches_reference_flow_source(name, direction):
         np.testing.assert_array_equal(got, want)
 
 
+PPZ = G.load("postprocess_golden.npz")
+
+
+@pytest.mark.parametrize("name", G.POSTPROCESS_CASES)
+def test_postprocess_oracle_matches_reference(name):
+    """Filters, mask and convolution kernel of ``FlowSource.post_process`` as the reference ran them
+    (bit-exact; ``polar`` goes through libm transcendentals and gets 1e-5)."""
+    import numpy  # the filter expressions of the golden cases name it, as transflow/utils.py does
+    from oracle import flow_cv as F
+    direction, filters, mask, kernel = G.postprocess_case_inputs(PPZ, name)
+    grays = [F.gray_from_bgr(f) for f in PPZ["clip"]]
+    want = PPZ[f"{name}/flows"]
+    for i in range(1, len(grays)):
+        left, right = (grays[i - 1], grays[i]) if direction == "forward" else (grays[i], grays[i - 1])
+        t = i / float(PPZ["framerate"])      # output_frame_index is incremented before post_process (source.py:321)
+        scalars = []
+        for key, expr in filters:
+            if key == "polar":
+                scalars.append((key, tuple(eval("lambda t,r,a: " + e, {"numpy": numpy}) for e in expr)))
+            else:
+                scalars.append((key, eval("lambda t: " + expr, {"numpy": numpy})(t)))
+        got = F.post_process(F.farneback(left, right), direction == "forward", mask=mask, kernel=kernel,
+                             filters=scalars, t=t)
+        assert got.dtype == want.dtype
+        if any(k == "polar" for k, _ in filters):
+            np.testing.assert_allclose(got, want[i - 1], atol=1e-5)
+        else:
+            np.testing.assert_array_equal(got, want[i - 1])
+
+
 def test_horn_schunck_own_blur_matches_cv2_blur():
     from oracle import flow_cv as F
     clip = FLOWZ["clip"]

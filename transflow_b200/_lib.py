@@ -48,6 +48,11 @@ class LayerConfigStruct(C.Structure):
     ]
 
 
+class FlowOpStruct(C.Structure):
+    """``tf_flow_op``: kind (0 scale, 1 threshold, 2 clip), strong (NumPy float64 scalar), value."""
+    _fields_ = [("kind", C.c_int), ("strong", C.c_int), ("value", C.c_double)]
+
+
 class PixmapStruct(C.Structure):
     _fields_ = [("pixels", C.c_void_p), ("channels", C.c_int32), ("frame_number", C.c_int32)]
 
@@ -83,6 +88,9 @@ SIGNATURES = {
     "tf_lk_run": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "tf_flow_postprocess": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp]),
     "tf_flow_postprocess_to": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "tf_flow_postprocess_ex": (_i, [_vp, C.POINTER(FlowOpStruct), _i, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "tf_flow_filters": (_i, [_vp, C.POINTER(FlowOpStruct), _i, _vp, _vp, _i, _i, _vp]),
+    "tf_flow_convolve": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "tf_device_malloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
     "tf_device_free": (_i, [_vp]),
     "tf_layer_create": (_i, [C.POINTER(_vp), _i, _i, C.POINTER(LayerConfigStruct)]),

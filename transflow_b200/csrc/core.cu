@@ -153,14 +153,125 @@ __device__ __forceinline__ float2 clip_flow(float2 f, int x, int y, int w, int h
     return f;
 }
 
-// backward direction: optional mask multiply + final clip.
+// Flow filters (transflow/flow/filters.py:36-68) as a short per-pixel program; NumPy's promotion rules decide
+// the arithmetic type: a Python scalar threshold is "weak" (everything stays float32), a NumPy float64 scalar
+// is "strong" (compare / scale in float64, result rounded to float32).
+struct FlowOps {
+    int n;
+    int kind[TF_MAX_FLOW_OPS];    // TF_FLOW_SCALE / TF_FLOW_THRESHOLD / TF_FLOW_CLIP
+    int strong[TF_MAX_FLOW_OPS];
+    float v32[TF_MAX_FLOW_OPS];
+    double v64[TF_MAX_FLOW_OPS];
+};
+
+__device__ __forceinline__ float2 apply_flow_ops(float2 f, const FlowOps& ops) {
+    for (int i = 0; i < ops.n; i++) {
+        const int kind = ops.kind[i];
+        if (kind == TF_FLOW_SCALE) {  // filters.py:41  flow *= expr(t)
+            if (ops.strong[i]) {
+                f.x = (float)((double)f.x * ops.v64[i]);
+                f.y = (float)((double)f.y * ops.v64[i]);
+            } else {
+                f.x = __fmul_rn(f.x, ops.v32[i]);
+                f.y = __fmul_rn(f.y, ops.v32[i]);
+            }
+            continue;
+        }
+        // numpy.linalg.norm(axis=1) on float32: sqrt(x*x + y*y), every step rounded to float32
+        const float norm = __fsqrt_rn(__fadd_rn(__fmul_rn(f.x, f.x), __fmul_rn(f.y, f.y)));
+        if (kind == TF_FLOW_THRESHOLD) {  // filters.py:49-53  flow[norm <= threshold] = 0
+            const bool hit = ops.strong[i] ? (double)norm <= ops.v64[i] : norm <= ops.v32[i];
+            if (hit) f = make_float2(0.f, 0.f);
+        } else {  // filters.py:61-68  flow *= threshold / norm where norm >= threshold (factors are float64)
+            if (ops.strong[i]) {
+                if ((double)norm >= ops.v64[i]) {
+                    const double fac = ops.v64[i] / (double)norm;
+                    f.x = (float)((double)f.x * fac);
+                    f.y = (float)((double)f.y * fac);
+                }
+            } else if (norm >= ops.v32[i]) {
+                const float fac = __fdiv_rn(ops.v32[i], norm);
+                f.x = __fmul_rn(f.x, fac);  // float32 x float32 in float64 is exact: one rounding, like NumPy
+                f.y = __fmul_rn(f.y, fac);
+            }
+        }
+    }
+    return f;
+}
+
+static int pack_flow_ops(const tf_flow_op* ops, int n_ops, FlowOps& out) {
+    TF_REQUIRE(n_ops >= 0 && n_ops <= TF_MAX_FLOW_OPS, TF_ERR_INVALID_ARG, "at most %d flow filters per call (got %d)",
+               TF_MAX_FLOW_OPS, n_ops);
+    TF_REQUIRE(n_ops == 0 || ops, TF_ERR_INVALID_ARG, "null flow filter list");
+    memset(&out, 0, sizeof(out));
+    out.n = n_ops;
+    for (int i = 0; i < n_ops; i++) {
+        TF_REQUIRE(ops[i].kind >= TF_FLOW_SCALE && ops[i].kind <= TF_FLOW_CLIP, TF_ERR_INVALID_ARG,
+                   "unknown flow filter kind %d", ops[i].kind);
+        out.kind[i] = ops[i].kind;
+        out.strong[i] = ops[i].strong != 0;
+        out.v32[i] = (float)ops[i].value;
+        out.v64[i] = ops[i].value;
+    }
+    return TF_OK;
+}
+
+// filters + mask only (the stage in front of the convolution kernel, source.py:339-343)
+__global__ void __launch_bounds__(256) k_flow_filters(const float2* __restrict__ flow, const float* __restrict__ mask,
+                                                      float2* __restrict__ out, size_t n, const FlowOps ops) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    float2 f = apply_flow_ops(flow[p], ops);
+    if (mask) {
+        float m = mask[p];
+        f.x = __fmul_rn(m, f.x);
+        f.y = __fmul_rn(m, f.y);
+    }
+    out[p] = f;
+}
+
+// scipy.signal.convolve2d(flow[..., c], kernel, mode="same", boundary="fill", fillvalue=0) (source.py:344-348):
+// float64 accumulation in kernel-index order, 'same' window centred at (k - 1) / 2.  The reference carries the
+// float64 result on; the public flow type is float32, so the value is rounded once -- except in the forward
+// direction, where only round-half-even of the clipped value survives (source.py:352): there the float32 value
+// is nudged to the float64 rounding result whenever the two would disagree.
+__global__ void __launch_bounds__(256) k_flow_convolve(const float2* __restrict__ flow, const double* __restrict__ ker,
+                                                       float2* __restrict__ out, int h, int w, int kh, int kw,
+                                                       int forward) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    const int oy = (kh - 1) / 2, ox = (kw - 1) / 2;
+    double sx = 0.0, sy = 0.0;
+    for (int j = 0; j < kh; j++) {
+        const int yy = y + oy - j;
+        for (int k = 0; k < kw; k++) {
+            const int xx = x + ox - k;
+            float2 v = make_float2(0.f, 0.f);
+            if ((unsigned)yy < (unsigned)h && (unsigned)xx < (unsigned)w) v = __ldg(flow + (size_t)yy * w + xx);
+            const double c = ker[j * kw + k];
+            sx = __dadd_rn(sx, __dmul_rn((double)v.x, c));
+            sy = __dadd_rn(sy, __dmul_rn((double)v.y, c));
+        }
+    }
+    float2 f = make_float2((float)sx, (float)sy);
+    if (forward) {
+        const double lox = -x, hix = w - 1 - x, loy = -y, hiy = h - 1 - y;
+        const double rx = rint(fmin(fmax(sx, lox), hix)), ry = rint(fmin(fmax(sy, loy), hiy));
+        if (rintf(fminf(fmaxf(f.x, (float)lox), (float)hix)) != (float)rx) f.x = (float)rx;
+        if (rintf(fminf(fmaxf(f.y, (float)loy), (float)hiy)) != (float)ry) f.y = (float)ry;
+    }
+    out[(size_t)y * w + x] = f;
+}
+
+// backward direction: optional filters + mask multiply + final clip.
 __global__ void __launch_bounds__(256) k_post_backward(const float2* __restrict__ flow, const float* __restrict__ mask,
-                                                       float2* __restrict__ out, int h, int w) {
+                                                       float2* __restrict__ out, int h, int w, const FlowOps ops) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;
     if (x >= w) return;
     size_t p = (size_t)y * w + x;
-    float2 f = flow[p];
+    float2 f = apply_flow_ops(flow[p], ops);
     if (mask) {
         float m = mask[p];
         f.x = __fmul_rn(m, f.x);
@@ -173,12 +284,13 @@ __global__ void __launch_bounds__(256) k_post_backward(const float2* __restrict_
 // numpy.put with duplicate targets keeps the LAST source in raster order (quirk Q7).
 __global__ void __launch_bounds__(256) k_post_forward_scatter(const float2* __restrict__ flow,
                                                               const float* __restrict__ mask,
-                                                              int* __restrict__ owner, int h, int w) {
+                                                              int* __restrict__ owner, int h, int w,
+                                                              const FlowOps ops) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;
     if (x >= w) return;
     int p = y * w + x;
-    float2 f = flow[p];
+    float2 f = apply_flow_ops(flow[p], ops);
     if (mask) {
         float m = mask[p];
         f.x = __fmul_rn(m, f.x);
@@ -211,26 +323,60 @@ __global__ void __launch_bounds__(256) k_post_forward_gather(float2* __restrict_
     out[p] = f;  // already inside the frame: the final clip is the identity here
 }
 
-extern "C" int tf_flow_postprocess_to(float* flow, const float* mask, int forward, int32_t* owner, float* out,
-                                      int height, int width, void* stream) {
+extern "C" int tf_flow_postprocess_ex(float* flow, const tf_flow_op* ops, int n_ops, const float* mask, int forward,
+                                      int32_t* owner, float* out, int height, int width, void* stream) {
     TF_REQUIRE(flow, TF_ERR_INVALID_ARG, "tf_flow_postprocess: null flow");
     TF_REQUIRE(height > 0 && width > 0, TF_ERR_SHAPE, "tf_flow_postprocess: bad shape %dx%d", height, width);
     TF_REQUIRE(!forward || owner, TF_ERR_INVALID_ARG, "tf_flow_postprocess: forward direction needs the owner plane");
     if (int e = require_sm100()) return e;
+    FlowOps packed;
+    if (int e = pack_flow_ops(ops, n_ops, packed)) return e;
     if (!out) out = flow;
     dim3 grid(ceil_div(width, 256), height);
     cudaStream_t st = as_stream(stream);
     if (!forward) {
         k_post_backward<<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(flow), mask, reinterpret_cast<float2*>(out),
-                                              height, width);
+                                              height, width, packed);
         TF_LAUNCHED();
     } else {
         ScopedKernelTimer timer(TFK_POST_FORWARD, st);
-        k_post_forward_scatter<<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(flow), mask, owner, height, width);
+        k_post_forward_scatter<<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(flow), mask, owner, height, width,
+                                                     packed);
         TF_LAUNCHED();
         k_post_forward_gather<<<grid, 256, 0, st>>>(reinterpret_cast<float2*>(out), owner, height, width);
         TF_LAUNCHED();
     }
+    return TF_OK;
+}
+
+extern "C" int tf_flow_postprocess_to(float* flow, const float* mask, int forward, int32_t* owner, float* out,
+                                      int height, int width, void* stream) {
+    return tf_flow_postprocess_ex(flow, nullptr, 0, mask, forward, owner, out, height, width, stream);
+}
+
+extern "C" int tf_flow_filters(const float* flow, const tf_flow_op* ops, int n_ops, const float* mask, float* out,
+                               int height, int width, void* stream) {
+    TF_REQUIRE(flow && out, TF_ERR_INVALID_ARG, "tf_flow_filters: null buffer");
+    TF_REQUIRE(height > 0 && width > 0, TF_ERR_SHAPE, "tf_flow_filters: bad shape %dx%d", height, width);
+    if (int e = require_sm100()) return e;
+    FlowOps packed;
+    if (int e = pack_flow_ops(ops, n_ops, packed)) return e;
+    size_t n = (size_t)height * width;
+    k_flow_filters<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float2*>(flow), mask, reinterpret_cast<float2*>(out), n, packed);
+    TF_LAUNCHED();
+    return TF_OK;
+}
+
+extern "C" int tf_flow_convolve(const float* flow, const double* kernel, int kh, int kw, int forward, float* out,
+                                int height, int width, void* stream) {
+    TF_REQUIRE(flow && kernel && out, TF_ERR_INVALID_ARG, "tf_flow_convolve: null buffer");
+    TF_REQUIRE(flow != out, TF_ERR_INVALID_ARG, "tf_flow_convolve: cannot run in place");
+    TF_REQUIRE(height > 0 && width > 0 && kh > 0 && kw > 0, TF_ERR_SHAPE, "tf_flow_convolve: bad shape");
+    if (int e = require_sm100()) return e;
+    k_flow_convolve<<<dim3(ceil_div(width, 256), height), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float2*>(flow), kernel, reinterpret_cast<float2*>(out), height, width, kh, kw, forward);
+    TF_LAUNCHED();
     return TF_OK;
 }
 

@@ -130,6 +130,8 @@ struct FbLevel {
     float* tx;
     int* sy;
     float* ty;
+    int br_rows, br_pitch;  // fused blur+resize: largest footprint of a BR_TX x BR_TY tile (0 = use the two passes)
+    size_t br_smem;
     float* img;     // pyramid image of the frame prepared last (h x w)
     void* R[2];     // polynomial expansion per slot, 5*h*w elements (float or __half) in the "4+1" layout
     float2* flow;   // per-level flow (the finest level writes into the caller's buffer)
@@ -208,6 +210,126 @@ __global__ void __launch_bounds__(256) k_fb_vpass(const float* __restrict__ T, f
         b = fmaf(g, T[(size_t)reflect101(s1 + j - rad, H) * w + x], b);
     }
     img[(size_t)y * w + x] = a * (1.f - t) + b * t;
+}
+
+// hpass + vpass fused for one pyramid level: a block produces BR_TX x BR_TY level pixels from the gray
+// footprint they depend on (staged in shared memory as bytes, BORDER_REFLECT_101 applied while loading),
+// with the SAME operation order as the two separate passes, so the result is bit-identical to them.
+#define BR_TX 32
+#define BR_TY 8
+#define FB_MAX_FUSED_LEVELS 8
+struct BrLevel {
+    const float* gk;
+    const int* sx;
+    const float* tx;
+    const int* sy;
+    const float* ty;
+    float* img;
+    int w, h, ksz, fr_max, fc_pitch, tiles_x, tile_end;  // tile_end: running total of tiles up to this level
+};
+struct BrArgs {
+    BrLevel lv[FB_MAX_FUSED_LEVELS];
+    int n;
+};
+// All pyramid levels that need a blur go in ONE launch (coarsest = widest Gaussian first): every tile is a short
+// chain of dependent memory round trips, and the levels' chains overlap instead of running back to back.
+__global__ void __launch_bounds__(BR_TX* BR_TY) k_fb_blur_resize(const uint8_t* __restrict__ gray, int H, int W,
+                                                                  const __grid_constant__ BrArgs args) {
+    extern __shared__ __align__(16) unsigned char br_smem[];
+    int li = 0;
+    while (li + 1 < args.n && (int)blockIdx.x >= args.lv[li].tile_end) li++;
+    const BrLevel& A = args.lv[li];
+    const int tile = blockIdx.x - (li ? args.lv[li - 1].tile_end : 0);
+    const float* __restrict__ gk = A.gk;
+    const int* __restrict__ sx = A.sx;
+    const float* __restrict__ tx = A.tx;
+    const int* __restrict__ sy = A.sy;
+    const float* __restrict__ ty = A.ty;
+    float* __restrict__ img = A.img;
+    const int w = A.w, h = A.h, ksz = A.ksz, fr_max = A.fr_max, fc_pitch = A.fc_pitch;
+    float* sT = reinterpret_cast<float*>(br_smem);                   // [fr_max][BR_TX]
+    float* sG = sT + fr_max * BR_TX;                                 // [ksz]
+    unsigned char* sS = reinterpret_cast<unsigned char*>(sG + ksz);  // [fr_max][fc_pitch]
+    const int tid = threadIdx.x;
+    const int x0 = (tile % A.tiles_x) * BR_TX, y0 = (tile / A.tiles_x) * BR_TY;
+    const int xl = min(x0 + BR_TX - 1, w - 1), yl = min(y0 + BR_TY - 1, h - 1);
+    const int rad = ksz >> 1;
+    const int c0 = sx[x0] - rad, r0 = sy[y0] - rad;
+    const int ncols = sx[xl] + 1 + rad - c0 + 1, nrows = sy[yl] + 1 + rad - r0 + 1;
+    for (int i = tid; i < ksz; i += BR_TX * BR_TY) sG[i] = gk[i];
+    int off = 0;  // column of the footprint's first pixel inside its staged row
+    if (c0 >= 0 && ((c0 & ~3) + ((((c0 & 3) + ncols + 3) >> 2) << 2)) <= W && (W & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(gray) & 3) == 0) {
+        // tiles inside the frame: aligned 32-bit loads, four independent requests per thread in flight
+        off = c0 & 3;
+        const int nw = (off + ncols + 3) >> 2, total = nrows * nw;
+        constexpr int NTH = BR_TX * BR_TY;
+        for (int base = tid; base < total; base += 4 * NTH) {
+            uint32_t v[4];
+            int fr[4], q[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int i = base + k * NTH;
+                fr[k] = i / nw;
+                q[k] = i - fr[k] * nw;
+                if (i < total)
+                    v[k] = __ldg(reinterpret_cast<const uint32_t*>(gray + (size_t)reflect101(r0 + fr[k], H) * W + (c0 - off)) + q[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (base + k * NTH < total) reinterpret_cast<uint32_t*>(sS + fr[k] * fc_pitch)[q[k]] = v[k];
+        }
+    } else {
+        // tiles touching a border: one warp per footprint row, byte loads with reflected columns
+        const int lane = tid & 31;
+        for (int fr = tid >> 5; fr < nrows; fr += (BR_TX * BR_TY) / 32) {
+            const uint8_t* src = gray + (size_t)reflect101(r0 + fr, H) * W;
+            unsigned char* dst = sS + fr * fc_pitch;
+            for (int fc = lane; fc < ncols; fc += 32) dst[fc] = __ldg(src + reflect101(c0 + fc, W));
+        }
+    }
+    __syncthreads();
+    // horizontal Gaussian at the two source columns of every output column + horizontal lerp
+    {
+        const int ox = tid & (BR_TX - 1);
+        const int x = min(x0 + ox, w - 1);
+        const int lc = sx[x] - sx[x0];
+        const float t = tx[x];
+        for (int fr = tid / BR_TX; fr < nrows; fr += BR_TY) {
+            const unsigned char* row = sS + fr * fc_pitch + off + lc;
+            float a = 0.f, b = 0.f;
+            float v = (float)row[0];
+            for (int j = 0; j < ksz; j++) {
+                float g = sG[j];
+                float nv = (float)row[j + 1];
+                a = fmaf(g, v, a);
+                b = fmaf(g, nv, b);
+                v = nv;
+            }
+            sT[fr * BR_TX + ox] = a * (1.f - t) + b * t;
+        }
+    }
+    __syncthreads();
+    // vertical Gaussian at the two source rows + vertical lerp
+    {
+        const int ox = tid & (BR_TX - 1), oy = tid / BR_TX;
+        const int x = x0 + ox, y = y0 + oy;
+        if (x < w && y < h) {
+            const int lr = sy[y] - sy[y0];
+            const float t = ty[y];
+            const float* col = sT + lr * BR_TX + ox;
+            float a = 0.f, b = 0.f;
+            float v = col[0];
+            for (int j = 0; j < ksz; j++) {
+                float g = sG[j];
+                float nv = col[(j + 1) * BR_TX];
+                a = fmaf(g, v, a);
+                b = fmaf(g, nv, b);
+                v = nv;
+            }
+            img[(size_t)y * w + x] = a * (1.f - t) + b * t;
+        }
+    }
 }
 
 // Polynomial expansion (FarnebackPolyExp): separable (2n+1)^2 window, replicate borders.
@@ -339,7 +461,11 @@ __global__ void __launch_bounds__(256) k_fb_polyexp(const float* __restrict__ im
     __syncthreads();
     // horizontal pass: TY rows x (TX / 4) column groups = 256 work items
     {
-        int ly = tid / (TX / 4), gx = (tid % (TX / 4)) * 4;
+        // a warp covers 8 column groups x 4 rows: with the odd pitch SP the 32 lanes read 32
+        // distinct banks (16 groups x 2 rows would collide pairwise)
+        static_assert(TX == 64 && TY == 16 && (SP & 1) == 1, "lane mapping of the horizontal pass");
+        const int lane = tid & 31, wrp = tid >> 5;
+        int ly = (lane >> 3) + 4 * (wrp >> 1), gx = ((lane & 7) + 8 * (wrp & 1)) * 4;
         float w0[4 + 2 * N], w1[4 + 2 * N], w2[4 + 2 * N];
 #pragma unroll
         for (int j = 0; j < 4 + 2 * N; j++) {
@@ -464,6 +590,8 @@ __global__ void __launch_bounds__(256) k_fb_box_h_solve(const double* __restrict
     flow[(size_t)y * w + x] = f;
 }
 
+static int g_fb_two_pass = 0;  // tf_farneback_tune(1, ..): separate blur passes instead of the fused kernel
+
 #include "fb_iter.cuh"
 #include "fb_tile.cuh"
 #include "fb_half.cuh"
@@ -471,6 +599,7 @@ __global__ void __launch_bounds__(256) k_fb_box_h_solve(const double* __restrict
 int g_fbh_rows = 0;
 extern "C" int tf_farneback_tune(int key, int value) {
     if (key == 0) g_fbh_rows = value;
+    else if (key == 1) g_fb_two_pass = value;
     else return fail(TF_ERR_INVALID_ARG, "tf_farneback_tune: unknown key %d", key);
     return TF_OK;
 }
@@ -551,9 +680,18 @@ extern "C" int tf_farneback_create(tf_farneback** out, int height, int width, do
         std::vector<float> t;
         if (int e = upload(&L.gk, gaussian_kernel(L.ksz, L.sigma))) return bail(e);
         linear_table(L.w, width, s, t);
+        int fc = 0, fr = 0;
+        for (int a0 = 0; a0 < L.w; a0 += BR_TX)
+            fc = std::max(fc, s[std::min(a0 + BR_TX - 1, L.w - 1)] - s[a0] + 2 * (L.ksz / 2) + 2);
         if (int e = upload(&L.sx, s)) return bail(e);
         if (int e = upload(&L.tx, t)) return bail(e);
         linear_table(L.h, height, s, t);
+        for (int a0 = 0; a0 < L.h; a0 += BR_TY)
+            fr = std::max(fr, s[std::min(a0 + BR_TY - 1, L.h - 1)] - s[a0] + 2 * (L.ksz / 2) + 2);
+        L.br_rows = fr;
+        L.br_pitch = ((fc + 3) & ~3) + 4;  // + room for the alignment offset of the 32-bit loads
+        L.br_smem = (size_t)fr * BR_TX * 4 + (size_t)L.ksz * 4 + (size_t)fr * L.br_pitch;
+        if (L.br_smem > 96 * 1024) L.br_rows = 0;  // absurdly wide Gaussians: keep the two-pass kernels
         if (int e = upload(&L.sy, s)) return bail(e);
         if (int e = upload(&L.ty, t)) return bail(e);
         size_t n = (size_t)L.w * L.h;
@@ -609,10 +747,48 @@ static int launch_polyexp(const tf_farneback* h, const FbLevel& L, int slot, con
     return TF_OK;
 }
 
-static int prepare_level(tf_farneback* h, FbLevel& L, int slot, const uint8_t* gray, cudaStream_t st) {
+// One launch for the blur + resize of every level that needs it; false if some level must use the two passes.
+static bool fused_blur_ok(const tf_farneback* h) {
+    if (g_fb_two_pass || h->lv.size() > FB_MAX_FUSED_LEVELS) return false;
+    for (auto& L : h->lv)
+        if (L.br_rows <= 0) return false;
+    return true;
+}
+
+static int blur_levels(tf_farneback* h, const uint8_t* gray, cudaStream_t st) {
+    BrArgs args;
+    args.n = 0;
+    size_t smem = 0;
+    int tiles = 0;
+    for (auto& L : h->lv) {  // coarse -> fine
+        bool fuse = L.w == h->W && L.h == h->H && L.ksz == 3 && L.sigma <= 0;
+        if (fuse) continue;  // the finest level's 3x3 blur lives in the polynomial expansion kernel
+        BrLevel& B = args.lv[args.n++];
+        B.gk = L.gk; B.sx = L.sx; B.tx = L.tx; B.sy = L.sy; B.ty = L.ty; B.img = L.img;
+        B.w = L.w; B.h = L.h; B.ksz = L.ksz; B.fr_max = L.br_rows; B.fc_pitch = L.br_pitch;
+        B.tiles_x = ceil_div(L.w, BR_TX);
+        tiles += B.tiles_x * ceil_div(L.h, BR_TY);
+        B.tile_end = tiles;
+        smem = std::max(smem, L.br_smem);
+    }
+    if (!args.n) return TF_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TF_CUDA(cudaFuncSetAttribute(k_fb_blur_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+    }
+    k_fb_blur_resize<<<tiles, BR_TX * BR_TY, smem, st>>>(gray, h->H, h->W, args);
+    TF_LAUNCHED();
+    return TF_OK;
+}
+
+static int prepare_level(tf_farneback* h, FbLevel& L, int slot, const uint8_t* gray, cudaStream_t st,
+                         bool blurred = false) {
     // the finest level (identity resize, sigma 0 -> fixed [1/4, 1/2, 1/4] taps) is fused into polyexp
     bool fuse = L.w == h->W && L.h == h->H && L.ksz == 3 && L.sigma <= 0 && h->W >= 2 && h->H >= 2;
-    if (!fuse) {
+    if (!fuse && blurred) {
+        // the batched blur launch (blur_levels) already produced L.img
+    } else if (!fuse) {
         k_fb_hpass<<<dim3(ceil_div(L.w, 256), h->H), 256, 0, st>>>(gray, h->T, L.gk, L.sx, L.tx, h->H, h->W, L.w, L.ksz);
         TF_LAUNCHED();
         k_fb_vpass<<<dim3(ceil_div(L.w, 256), L.h), 256, 0, st>>>(h->T, L.img, L.gk, L.sy, L.ty, h->H, L.w, L.h, L.ksz);
@@ -626,8 +802,11 @@ extern "C" int tf_farneback_prepare(tf_farneback* h, int slot, const uint8_t* gr
     TF_REQUIRE(h && gray, TF_ERR_INVALID_ARG, "tf_farneback_prepare: null argument");
     TF_REQUIRE(slot == 0 || slot == 1, TF_ERR_INVALID_ARG, "tf_farneback_prepare: slot must be 0 or 1");
     cudaStream_t st = as_stream(stream);
+    const bool batched = fused_blur_ok(h);
+    if (batched)
+        if (int e = blur_levels(h, gray, st)) return e;
     for (auto& L : h->lv)
-        if (int e = prepare_level(h, L, slot, gray, st)) return e;
+        if (int e = prepare_level(h, L, slot, gray, st, batched)) return e;
     return TF_OK;
 }
 
@@ -733,8 +912,11 @@ extern "C" int tf_farneback_step(tf_farneback* h, int new_slot, const uint8_t* g
     // stream (the previous pair's solve read that slot; `gray` was produced there) has finished
     TF_CUDA(cudaEventRecord(h->ev_start, st));
     TF_CUDA(cudaStreamWaitEvent(h->aux, h->ev_start, 0));
+    const bool batched = fused_blur_ok(h);
+    if (batched)
+        if (int e = blur_levels(h, gray, h->aux)) return e;
     for (size_t li = 0; li < h->lv.size(); li++) {
-        if (int e = prepare_level(h, h->lv[li], new_slot, gray, h->aux)) return e;
+        if (int e = prepare_level(h, h->lv[li], new_slot, gray, h->aux, batched)) return e;
         TF_CUDA(cudaEventRecord(h->ev_level[li], h->aux));
     }
     float2* out = reinterpret_cast<float2*>(flow);

@@ -1,16 +1,31 @@
-"""Flow filters (``transflow/flow/filters.py``): in-place elementwise edits of the flow with
-expressions of the time ``t``.  Next-tier row 8f-1: they run on the device tensor (so the flow
-never returns to the host between estimation and accumulation) but as plain tensor
-expressions for now, not hand-written kernels."""
+"""Flow filters (``transflow/flow/filters.py``): in-place edits of the flow with expressions of the time ``t``.
+
+``scale``, ``threshold`` and ``clip`` are one scalar per frame and run inside the post-process kernel
+(``tf_flow_postprocess_ex``: filters -> mask -> clip / scatter in ONE pass over the flow), with
+NumPy's promotion rules reproduced (a Python scalar keeps float32 arithmetic, a NumPy float64 scalar promotes).
+``polar`` evaluates arbitrary user expressions of per-pixel arrays ``(r, a)``: those run as device tensor
+expressions between two kernel calls.
+"""
 import torch
 
+from .. import ops
 from ..utils import parse_lambda_expression
 
 
 class FlowFilter:
+    #: name of the fused elementwise op, None when the filter needs tensor expressions
+    kind: str | None = None
+
+    def op(self, t: float):
+        """-> ("scale" | "threshold" | "clip", scalar for this frame), consumed by ``ops.PostProcess``."""
+        raise NotImplementedError()
 
     def apply(self, flow: torch.Tensor, t: float) -> None:
-        raise NotImplementedError()
+        """Stand-alone, in place on the device flow (same arithmetic as the fused path)."""
+        h, w = flow.shape[:2]
+        arr, n = ops._pack_flow_ops([self.op(t)])
+        lib = ops._lib.load()
+        ops.check(lib.tf_flow_filters(ops.ptr(flow), arr, n, None, ops.ptr(flow), h, w, ops.stream_ptr()))
 
     @classmethod
     def from_args(cls, filter_name: str, filter_args: tuple):
@@ -24,35 +39,32 @@ class FlowFilter:
         return klass(filter_args)
 
 
-class ScaleFlowFilter(FlowFilter):
+class _ScalarFlowFilter(FlowFilter):
     def __init__(self, args):
         self.expr = parse_lambda_expression(args[0])
 
-    def apply(self, flow, t):
-        flow *= self.expr(t)
+    def op(self, t):
+        return self.kind, self.expr(t)
 
 
-class ThresholdFlowFilter(FlowFilter):
-    def __init__(self, args):
-        self.expr = parse_lambda_expression(args[0])
-
-    def apply(self, flow, t):
-        norm = torch.linalg.vector_norm(flow, dim=2)
-        flow[norm <= self.expr(t)] = 0
+class ScaleFlowFilter(_ScalarFlowFilter):
+    """``flow *= expr(t)`` (filters.py:36-42)."""
+    kind = "scale"
 
 
-class ClipFlowFilter(FlowFilter):
-    def __init__(self, args):
-        self.expr = parse_lambda_expression(args[0])
+class ThresholdFlowFilter(_ScalarFlowFilter):
+    """``flow[norm <= expr(t)] = 0`` (filters.py:45-54)."""
+    kind = "threshold"
 
-    def apply(self, flow, t):
-        threshold = self.expr(t)
-        norm = torch.linalg.vector_norm(flow, dim=2)
-        factors = torch.where(norm >= threshold, threshold / norm, torch.ones_like(norm))
-        flow *= factors.unsqueeze(2)
+
+class ClipFlowFilter(_ScalarFlowFilter):
+    """``flow *= expr(t) / norm`` where ``norm >= expr(t)`` (filters.py:57-70)."""
+    kind = "clip"
 
 
 class PolarFlowFilter(FlowFilter):
+    """Polar re-parametrisation with user expressions of ``(t, r, a)`` arrays (filters.py:73-87)."""
+
     def __init__(self, args):
         self.expr_radius = parse_lambda_expression(args[0], ("t", "r", "a"))
         self.expr_theta = parse_lambda_expression(args[1], ("t", "r", "a"))

@@ -289,19 +289,33 @@ class FlowSource:
     def post_process(self, raw):
         """filters -> mask -> kernel -> [forward: clip, round, scatter] -> clip, on the device.
 
-        The mask multiply and the kernel convolution produce a new tensor (as NumPy does in the
-        reference), everything else mutates ``raw`` in place.
+        Runs of scalar filters (scale / threshold / clip) are folded into the post-process kernel together with
+        the mask multiply; a ``polar`` filter (arbitrary array expressions) splits the run.  With a convolution
+        kernel the order of the reference is kept: filters + mask, float64 convolution, then the clip / scatter.
         """
         flow = raw if isinstance(raw, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(raw)).cuda()
+        pending = []
+        t = self.t
         for flt in self.flow_filters:
-            flt.apply(flow, self.t)
-        if self.mask is not None:
-            flow = flow * torch.from_numpy(np.ascontiguousarray(self.mask, dtype=np.float32)).to(flow.device)
-        if self.kernel is not None:
-            flow = _convolve_same(flow, self.kernel)
+            if flt.kind is not None and len(pending) < ops.MAX_FLOW_OPS:
+                pending.append(flt.op(t))
+                continue
+            if pending:
+                arr, n = ops._pack_flow_ops(pending)
+                ops.check(ops._lib.load().tf_flow_filters(ops.ptr(flow), arr, n, None, ops.ptr(flow), self.height,
+                                                          self.width, ops.stream_ptr()))
+                pending = []
+            if flt.kind is not None:
+                pending.append(flt.op(t))
+            else:
+                flt.apply(flow, t)
         if self._post is None:
-            self._post = ops.PostProcess(self.height, self.width, self.direction == FlowSource.Direction.FORWARD)
-        return self._post(flow)
+            mask = None
+            if self.mask is not None:
+                mask = torch.from_numpy(np.ascontiguousarray(self.mask, dtype=np.float32)).cuda()
+            self._post = ops.PostProcess(self.height, self.width, self.direction == FlowSource.Direction.FORWARD,
+                                         mask=mask, kernel=self.kernel)
+        return self._post(flow, ops=pending)
 
     @classmethod
     def from_args(cls, flow_path, use_mvs=False, mask_path=None, kernel_path=None, cv_config=None,
@@ -326,16 +340,3 @@ class FlowSource:
 
     def close(self):
         pass
-
-
-def _convolve_same(flow: torch.Tensor, kernel: np.ndarray) -> torch.Tensor:
-    """``scipy.signal.convolve2d(mode="same", boundary="fill")`` per channel (source.py:344-348).
-    Next-tier row 8f-1: a library convolution for now, not a hand-written kernel."""
-    k = torch.from_numpy(np.ascontiguousarray(kernel[::-1, ::-1].astype(np.float32))).to(flow.device)
-    kh, kw = k.shape
-    x = flow.permute(2, 0, 1).unsqueeze(1)
-    # 'same' output is centred with the (k-1)//2 convention of scipy for even sizes
-    pad = ((kw - 1) // 2, kw - 1 - (kw - 1) // 2, (kh - 1) // 2, kh - 1 - (kh - 1) // 2)
-    x = torch.nn.functional.pad(x, (pad[1], pad[0], pad[3], pad[2]))
-    y = torch.nn.functional.conv2d(x, k.view(1, 1, kh, kw))
-    return y.squeeze(1).permute(1, 2, 0).contiguous()

@@ -178,20 +178,59 @@ class LucasKanade:
         return out
 
 
-class PostProcess:
-    """``FlowSource.post_process`` (flow/sources/source.py:337-363) in place on a device flow."""
+FLOW_OP_KINDS = {"scale": 0, "threshold": 1, "clip": 2}
+MAX_FLOW_OPS = 8
 
-    def __init__(self, height, width, forward: bool, mask: torch.Tensor | None = None):
+
+def _pack_flow_ops(ops):
+    """[(kind name, scalar), ...] -> (ctypes array | None, count).  A NumPy floating scalar keeps NumPy's
+    "strong" float64 arithmetic, a Python number is weak (float32 next to the float32 flow)."""
+    import numpy as np
+    ops = list(ops or ())
+    if len(ops) > MAX_FLOW_OPS:
+        raise ValueError(f"at most {MAX_FLOW_OPS} elementwise flow filters per call, got {len(ops)}")
+    if not ops:
+        return None, 0
+    arr = (_lib.FlowOpStruct * len(ops))()
+    for slot, (kind, value) in zip(arr, ops):
+        slot.kind = FLOW_OP_KINDS[kind]
+        slot.strong = int(isinstance(value, np.floating) and not isinstance(value, np.float32))
+        slot.value = float(np.float32(value)) if isinstance(value, np.float32) else float(value)
+    return arr, len(ops)
+
+
+class PostProcess:
+    """``FlowSource.post_process`` (flow/sources/source.py:337-363) on a device flow: elementwise filters ->
+    mask -> [convolution kernel] -> [forward: clip, round, scatter] -> clip."""
+
+    def __init__(self, height, width, forward: bool, mask: torch.Tensor | None = None, kernel=None):
         self.lib = _lib.load()
         self.h, self.w, self.forward = int(height), int(width), bool(forward)
         self.mask = None if mask is None else _cuda(mask, torch.float32, "mask").reshape(self.h, self.w)
         self.owner = torch.zeros((self.h, self.w), dtype=torch.int32, device="cuda") if self.forward else None
+        self.kernel = None
+        if kernel is not None:      # scipy.signal.convolve2d promotes to float64 (source.py:345-347)
+            self.kernel = torch.as_tensor(kernel, dtype=torch.float64).contiguous().cuda()
+            if self.kernel.ndim != 2:
+                raise ValueError(f"the flow kernel must be 2-D, got shape {tuple(self.kernel.shape)}")
+            self._tmp = torch.empty((self.h, self.w, 2), dtype=torch.float32, device="cuda")
 
-    def __call__(self, flow: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
-        """In place by default; ``out`` (same shape, may be peer memory) receives the result instead."""
+    def __call__(self, flow: torch.Tensor, out: torch.Tensor | None = None, ops=None) -> torch.Tensor:
+        """In place by default; ``out`` (same shape, may be peer memory) receives the result instead.
+        ``ops``: [("scale" | "threshold" | "clip", scalar), ...] applied first, in order."""
         flow = _cuda(flow, torch.float32, "flow")
         if tuple(flow.shape) != (self.h, self.w, 2):
             raise ValueError(f"flow must be ({self.h}, {self.w}, 2), got {tuple(flow.shape)}")
-        check(self.lib.tf_flow_postprocess_to(ptr(flow), ptr(self.mask), int(self.forward), ptr(self.owner), ptr(out),
-                                              self.h, self.w, stream_ptr()))
+        arr, n = _pack_flow_ops(ops)
+        if self.kernel is not None:
+            check(self.lib.tf_flow_filters(ptr(flow), arr, n, ptr(self.mask), ptr(self._tmp), self.h, self.w,
+                                           stream_ptr()))
+            kh, kw = self.kernel.shape
+            check(self.lib.tf_flow_convolve(ptr(self._tmp), ptr(self.kernel), kh, kw, int(self.forward), ptr(flow),
+                                            self.h, self.w, stream_ptr()))
+            arr, n, mask = None, 0, None
+        else:
+            mask = self.mask
+        check(self.lib.tf_flow_postprocess_ex(ptr(flow), arr, n, ptr(mask), int(self.forward), ptr(self.owner),
+                                              ptr(out), self.h, self.w, stream_ptr()))
         return flow if out is None else out

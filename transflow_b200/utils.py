@@ -6,6 +6,7 @@ import re
 import warnings
 from typing import Callable
 
+import numpy  # noqa: F401  (user expressions may name it, as in transflow/utils.py)
 import numpy as np
 
 
