@@ -232,6 +232,19 @@ TF_API int tf_layer_poll_error(tf_layer* l, void* stream);
 TF_API int tf_layer_get_counters(const tf_layer* l, uint64_t* frames, int* introduced_once);
 TF_API int tf_layer_set_counters(tf_layer* l, uint64_t frames, int introduced_once);
 
+/* ---- float displacement map + bilinear remap (extension) ----------------------------
+ * The reference's WebGL variant in pixel units: extra/www/shaders/acc.frag:17-41 (map(p) = map_prev(p + f) + f
+ * with f = scale * boxblur(flow), then decay), extra/www/shaders/remap.frag:10-18 (out(p) = pixmap(p + map(p))),
+ * CLAMP_TO_EDGE, linear != 0 selects LINEAR sampling, else NEAREST (transflow.js:358-364).  The Python reference
+ * has no such mode; the kernels are checked against oracle/floatmap_np.py. */
+TF_API int tf_floatmap_accumulate(const float* map_prev, const float* flow, float* map_out, int height, int width,
+                                  float scale, float decay, int blur_size, int linear, void* stream);
+/* rgba_out (H, W, 4; alpha as the compositor's 0 / 1 flag) and / or rgb_inout (H, W, 3; composited like
+ * Compositor.render: opaque pixels overwrite, the first layer paints background_rgb = 0xRRGGBB elsewhere). */
+TF_API int tf_floatmap_remap(const float* map, const uint8_t* pixmap, int channels, int linear, uint8_t* rgba_out,
+                             uint8_t* rgb_inout, int first_layer, uint32_t background_rgb, int height, int width,
+                             void* stream);
+
 /* ---- multi-GPU flow hand-off over NVLink (frame pairs sharded across ranks) ---------------- */
 /* CUDA IPC plumbing so a producer rank's last flow kernel stores straight into the
  * accumulator rank's ring slot (peer memory), followed by a release flag. */

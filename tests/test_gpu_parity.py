@@ -592,3 +592,50 @@ def test_moveref_fast_path_equals_generic_kernel(reset, rgba_pixmap, tmp_path):
         base = np.indices((h, w), dtype=np.int32).transpose(1, 2, 0)
         frac = (d[..., :2] == base).all(axis=-1).mean()
         assert 0.05 < frac < 0.9          # some pixels were reset, not all
+
+
+# ------------------------------------------------------------------------------------------------
+# float displacement map + bilinear remap (extension a16) against the NumPy restatement of the shaders
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("settings", ["floatmap", "floatmap:nearest", "floatmap:linear:decay=0.05:blur=3:scale=1.5"])
+@pytest.mark.parametrize("channels", [3, 4])
+def test_floatmap_layer_matches_shader_restatement(settings, channels):
+    """Tolerances: the map is float32 arithmetic (1e-4 px over 4 frames); the 8-bit frame may differ by one level
+    where the interpolated value sits on a rounding boundary (and by more only where a NEAREST sample flips)."""
+    from oracle import floatmap_np as FM
+    from transflow_b200.compositor import Compositor
+    from transflow_b200.compositor.pixmap_source_interface import PixmapSourceInterface, StillQueue
+    from transflow_b200.config import LayerConfig
+    from transflow_b200.synthetic import cnoise_pixmap
+    h, w = 123, 211
+    rng = np.random.default_rng(9)
+    pix = cnoise_pixmap(h, w, 4)
+    if channels == 4:
+        alpha = np.where(rng.random((h, w)) < 0.2, 0, 255).astype(np.uint8)
+        pix = np.dstack([pix, alpha])
+    linear = "nearest" not in settings
+    kw = dict(scale=1.5, decay=0.05, blur_size=3) if "decay" in settings else dict(scale=1.0, decay=0.0, blur_size=1)
+    comp = Compositor.from_args(h, w, [LayerConfig(0, settings)], background_color="#102030")
+    comp.set_sources({0: [PixmapSourceInterface(StillQueue(pix), np.ones((h, w), bool))]})
+    want_map = np.zeros((h, w, 2), np.float32)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    for t in range(4):
+        flow = np.stack([2.5 * np.sin(yy / 17 + t) + rng.normal(0, 0.3, (h, w)),
+                         1.5 * np.cos(xx / 23 - t) + rng.normal(0, 0.3, (h, w))], axis=-1).astype(np.float32)
+        got = comp.step(flow).cpu().numpy()
+        want_map = FM.accumulate(want_map, flow, linear=linear, **kw)
+        got_map = comp.layers[0].map
+        if linear:
+            assert np.abs(got_map - want_map).max() < 1e-4
+        else:
+            assert (np.abs(got_map - want_map).max(axis=-1) > 1e-4).mean() < 1e-3
+        ref = FM.remap(got_map, pix, linear)          # remap checked on the same map
+        rgb, a = ref[..., :3].astype(np.int16), (ref[..., 3] if channels == 4 else np.full((h, w), 255))
+        want = np.where((a != 0)[..., None], rgb, np.array([0x10, 0x20, 0x30], np.int16))
+        diff = np.abs(got.astype(np.int16) - want)
+        assert (diff > 1).mean() < 2e-3, (diff > 1).mean()
+        rgba = comp.layers[0].render()
+        assert np.array_equal(rgba[..., 3] != 0, a != 0) or (np.not_equal(rgba[..., 3] != 0, a != 0)).mean() < 2e-3
+    import pickle
+    clone = pickle.loads(pickle.dumps(comp.layers[0]))
+    np.testing.assert_array_equal(clone.map, comp.layers[0].map)

@@ -281,4 +281,7 @@ class Layer:
         if config.classname == "sum":
             from .sum import SumLayer
             return SumLayer(*args)
+        if str(config.classname).split(":")[0] == "floatmap":     # extension
+            from .floatmap import FloatMapLayer
+            return FloatMapLayer(*args)
         raise ValueError(f"Unknown layer classname {config.classname}")
