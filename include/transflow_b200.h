@@ -163,6 +163,17 @@ TF_API int tf_flow_filters(const float* flow, const tf_flow_op* ops, int n_ops, 
 TF_API int tf_flow_convolve(const float* flow, const double* kernel, int kh, int kw, int forward, float* out,
                             int height, int width, void* stream);
 
+/* ---- Pipeline._update_flow: transflow/pipeline.py:492-507 ---------------------------------------------------
+ * Merge of several flow sources (FLOW_MERGING_FUNCTIONS, pipeline.py:149-158 + utils.py:359-381) and the integer
+ * upscale of a smaller flow (utils.upscale_array, utils.py:417-418), in NumPy's float32 arithmetic. */
+enum { TF_MERGE_FIRST = 0, TF_MERGE_SUM, TF_MERGE_AVERAGE, TF_MERGE_DIFFERENCE, TF_MERGE_PRODUCT, TF_MERGE_MASKBIN,
+       TF_MERGE_MASKLIN, TF_MERGE_ABSMAX };
+#define TF_MAX_MERGE_FLOWS 8
+/* flows: HOST array of n device pointers (H, W, 2); out may alias flows[0]. */
+TF_API int tf_flow_merge(const float* const* flows, int n, int mode, float* out, int height, int width, void* stream);
+/* (H, W, 2) -> (H * hf, W * wf, 2): vectors scaled by (wf, hf), then block-replicated. */
+TF_API int tf_flow_upscale(const float* flow, float* out, int height, int width, int wf, int hf, void* stream);
+
 /* ---- compositor: transflow/compositor/** ---------------------------------------------------- */
 enum { TF_LAYER_MOVEREF = 0, TF_LAYER_SUM = 1, TF_LAYER_STATIC = 2, TF_LAYER_INTRODUCTION = 3 };
 enum { TF_RESET_OFF = 0, TF_RESET_RANDOM = 1, TF_RESET_CONSTANT = 2, TF_RESET_LINEAR = 3 };

@@ -179,3 +179,45 @@ def post_process(flow: np.ndarray, forward: bool, mask=None, kernel=None, filter
     np.clip(flow[..., 0], lo_x, hi_x, out=flow[..., 0])
     np.clip(flow[..., 1], lo_y, hi_y, out=flow[..., 1])
     return flow
+
+
+def merge_flows(flows, mode: str) -> np.ndarray:
+    """``Pipeline.FLOW_MERGING_FUNCTIONS[mode](flows)`` (``pipeline.py:149-158``, helpers ``utils.py:359-381``).
+    Like the reference, ``maskbin`` overwrites the extra flows in place."""
+    def multiply_arrays(arrays):                                  # utils.py:359-365
+        if len(arrays) == 1:
+            return arrays[0]
+        out = np.multiply(arrays[0], arrays[1])
+        for a in arrays[2:]:
+            np.multiply(out, a, out)
+        return out
+
+    def binarize_arrays(arrays):                                  # utils.py:368-373
+        for a in arrays:
+            where = np.where(np.abs(a) > 0.2)
+            a[:, :] = 0
+            a[where] = 1
+        return arrays
+
+    def absmax(arrays):                                           # utils.py:376-381
+        w, h = arrays[0].shape[0:2]
+        stack = np.stack(arrays).reshape((2, w * h * 2))
+        argmax = np.argmax(np.abs(stack), axis=0).reshape((1, w * h * 2))
+        return np.take_along_axis(stack, argmax, 0).reshape(arrays[0].shape)
+
+    table = {
+        "first": lambda f: f[0],
+        "sum": lambda f: np.sum(f, axis=0),
+        "average": lambda f: np.sum(f, axis=0) / len(f),
+        "difference": lambda f: f[0] - sum(f[1:]),
+        "product": multiply_arrays,
+        "maskbin": lambda f: multiply_arrays([f[0]] + binarize_arrays(f[1:])),
+        "masklin": lambda f: multiply_arrays([f[0]] + [np.abs(x) for x in f[1:]]),
+        "absmax": absmax,
+    }
+    return table[mode](list(flows))
+
+
+def upscale_array(arr: np.ndarray, wf: int, hf: int) -> np.ndarray:
+    """``utils.upscale_array`` (``utils.py:417-418``)."""
+    return np.kron(arr * (wf, hf), np.ones((hf, wf, 1))).astype(arr.dtype)

@@ -288,6 +288,51 @@ def postprocess_cases(tmp):
     print("post-process cases:", len(cases))
 
 
+def merge_cases(tmp):
+    """The reference's flow merging functions (``pipeline.py:149-158``), ``utils.upscale_array`` and a ``.flow.zip``
+    written by the reference's own ``NumpyOutput`` (``output/numpy.py``) -- plus a check, here where the reference
+    is importable, that its ``ArchiveFlowSource`` reads an archive written by OUR ``NumpyOutput``."""
+    import shutil
+    from transflow.pipeline import Pipeline
+    from transflow.utils import upscale_array
+    from transflow.output.numpy import NumpyOutput as RefNumpyOutput
+    from transflow.flow.sources.source import FlowSource
+    rng = np.random.default_rng(21)
+    h, w = 10, 14
+    flows = [rng.uniform(-1, 1, (h, w, 2)).astype(np.float32) * s for s in (3, 0.4, 1)]
+    flows[1][rng.random((h, w)) < 0.3] = 0
+    out = {f"flow{i}": f for i, f in enumerate(flows)}
+    for mode, fn in Pipeline.FLOW_MERGING_FUNCTIONS.items():
+        for n in ((2,) if mode == "absmax" else (1, 2, 3)):
+            out[f"{mode}/{n}"] = np.array(fn([f.copy() for f in flows[:n]]))
+    out["upscale/3x2"] = upscale_array(flows[0].copy(), 3, 2)
+    np.savez_compressed(os.path.join(HERE, "merge_golden.npz"), **out)
+    meta = {"path": "clip.avi", "width": w, "height": h, "framerate": 25.0, "direction": 1, "seek_time": 0}
+    ref_zip = os.path.join(tmp, "ref.flow.zip")
+    o = RefNumpyOutput(ref_zip, replace=True)
+    o.write_meta(meta)
+    for f in flows:
+        o.write_array(f)
+    o.close()
+    shutil.copy(ref_zip, os.path.join(HERE, "ref_archive.flow.zip"))
+    from transflow_b200.output import NumpyOutput
+    ours = os.path.join(tmp, "ours.flow.zip")
+    o = NumpyOutput(ours, replace=True)
+    o.write_meta(meta)
+    for f in flows:
+        o.write_array(f)
+    o.close()
+    with FlowSource.from_args(ours) as src:      # the reference reads our archive
+        assert (src.width, src.height, src.framerate, src.direction.value) == (w, h, 25.0, 1)
+        # the reference's archive Builder.build never resolves the frame range (archive.py:25-36 does not chain to
+        # FlowSource.Builder.build), so its iterator has no end: read the three frames explicitly
+        back = [np.array(next(src)) for _ in range(3)]
+    from oracle import flow_cv as F
+    for got, f in zip(back, flows):
+        assert np.array_equal(got, F.post_process(f.copy(), False))     # backward: the final clip only
+    print("merge cases:", len(out), "- reference read", len(back), "flows of our archive")
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     with tempfile.TemporaryDirectory() as tmp:
@@ -298,6 +343,8 @@ if __name__ == "__main__":
             flow_cases(tmp)
         if not only or "postprocess" in only:
             postprocess_cases(tmp)
+        if not only or "merge" in only:
+            merge_cases(tmp)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -1,5 +1,7 @@
 """GPU parity tests: every call goes through the C ABI (ctypes) and is checked against the
 CPU oracle (oracle/, pinned in tests/test_oracle.py) and the committed golden vectors."""
+import os
+
 import numpy as np
 import pytest
 
@@ -639,3 +641,63 @@ def test_floatmap_layer_matches_shader_restatement(settings, channels):
     import pickle
     clone = pickle.loads(pickle.dumps(comp.layers[0]))
     np.testing.assert_array_equal(clone.map, comp.layers[0].map)
+
+
+# ------------------------------------------------------------------------------------------------
+# Pipeline._update_flow pieces: flow merging, integer upscale, .flow.zip archives
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["first", "sum", "average", "difference", "product", "maskbin", "masklin", "absmax"])
+def test_merge_and_upscale_match_reference(mode):
+    from transflow_b200 import ops
+    z = G.load("merge_golden.npz")
+    for n in ((2,) if mode == "absmax" else (1, 2, 3)):
+        got = ops.merge_flows([dev(z[f"flow{i}"]) for i in range(n)], mode).cpu().numpy()
+        np.testing.assert_array_equal(got, z[f"{mode}/{n}"])
+    np.testing.assert_array_equal(ops.upscale_flow(dev(z["flow0"]), 3, 2).cpu().numpy(), z["upscale/3x2"])
+    with pytest.raises(ValueError):        # NumPy's reshape((2, ...)) raises ValueError for any other count
+        ops.merge_flows([dev(z["flow0"])] * 3, "absmax")
+
+
+def test_flow_archive_source_reads_reference_archive():
+    from transflow_b200.flow import FlowSource
+    z = G.load("merge_golden.npz")
+    path = os.path.join(G.GOLDEN_DIR, "ref_archive.flow.zip")
+    with FlowSource.from_args(path) as src:
+        assert (src.width, src.height, src.framerate, src.length) == (14, 10, 25.0, 3)
+        assert src.direction == FlowSource.Direction.BACKWARD
+        flows = list(src)
+    assert len(flows) == 3
+    for i, got in enumerate(flows):
+        np.testing.assert_array_equal(got, F.post_process(z[f"flow{i}"].copy(), False))
+
+
+def test_pipeline_merges_and_exports_flow(tmp_path):
+    """Two flow sources merged by "sum", exported as .flow.zip, and the archive replayed gives the same frames."""
+    import zipfile
+    from transflow_b200.pipeline import Config, Pipeline
+    from transflow_b200.config import LayerConfig, PixmapSourceConfig
+    from transflow_b200.flow.sources.cv import ArrayCapture
+    from transflow_b200.synthetic import synthetic_clip
+    h, w = 96, 128
+    clip = synthetic_clip(h, w, 4, seed=5)
+    frames = {}
+    archive = str(tmp_path / "run.flow.zip")
+    cfg = Config(flow_path=ArrayCapture(clip), extra_flow_paths=[ArrayCapture(clip[::-1].copy())],
+                 flows_merging_function="sum", export_flow=archive, direction="backward",
+                 pixmap_sources=[PixmapSourceConfig("cnoise", layers=[0])], layers=[LayerConfig(0, "moveref")],
+                 output_path=lambda i, rgb: frames.__setitem__(i, rgb.copy()), seed=3)
+    p = Pipeline(cfg)
+    p.run()
+    p.close()
+    assert len(frames) == 3
+    names = zipfile.ZipFile(archive).namelist()
+    assert sorted(names) == ["000000000.npy", "000000001.npy", "000000002.npy", "meta.json"]
+    replay = {}
+    cfg2 = Config(flow_path=archive, direction="backward", pixmap_sources=[PixmapSourceConfig("cnoise", layers=[0])],
+                  layers=[LayerConfig(0, "moveref")], output_path=lambda i, rgb: replay.__setitem__(i, rgb.copy()),
+                  seed=3)
+    p2 = Pipeline(cfg2)
+    p2.run()
+    p2.close()
+    for i in frames:
+        np.testing.assert_array_equal(frames[i], replay[i])

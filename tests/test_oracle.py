@@ -1,5 +1,7 @@
 """CPU: pin the oracle against the golden vectors produced by the real reference and
 against the live cv2 build."""
+import os
+
 import numpy as np
 import pytest
 
@@ -153,6 +155,47 @@ def test_postprocess_oracle_matches_reference(name):
             np.testing.assert_allclose(got, want[i - 1], atol=1e-5)
         else:
             np.testing.assert_array_equal(got, want[i - 1])
+
+
+MERGE_MODES = ["first", "sum", "average", "difference", "product", "maskbin", "masklin", "absmax"]
+
+
+@pytest.mark.parametrize("mode", MERGE_MODES)
+def test_merge_oracle_matches_reference(mode):
+    from oracle import flow_cv as F
+    z = G.load("merge_golden.npz")
+    for n in ((2,) if mode == "absmax" else (1, 2, 3)):
+        got = F.merge_flows([z[f"flow{i}"].copy() for i in range(n)], mode)
+        np.testing.assert_array_equal(got, z[f"{mode}/{n}"])
+        assert got.dtype == z[f"{mode}/{n}"].dtype
+    np.testing.assert_array_equal(F.upscale_array(z["flow0"].copy(), 3, 2), z["upscale/3x2"])
+
+
+def test_flow_archive_writer_matches_reference_format(tmp_path):
+    """Our NumpyOutput writes what the reference's NumpyOutput wrote (tests/golden/ref_archive.flow.zip): same
+    member names, same meta.json, identical arrays."""
+    import json
+    import zipfile
+    from transflow_b200.output import NumpyOutput
+    from transflow_b200.output.zip import find_unique_path
+    z = G.load("merge_golden.npz")
+    ref = zipfile.ZipFile(os.path.join(G.GOLDEN_DIR, "ref_archive.flow.zip"))
+    meta = json.loads(ref.read("meta.json").decode())
+    path = str(tmp_path / "out.flow.zip")
+    out = NumpyOutput(path, replace=True)
+    out.write_meta(meta)
+    for i in range(3):
+        out.write_array(z[f"flow{i}"])
+    out.close()
+    mine = zipfile.ZipFile(path)
+    assert sorted(mine.namelist()) == sorted(ref.namelist())
+    assert json.loads(mine.read("meta.json").decode()) == meta
+    for name in ref.namelist():
+        if name.endswith(".npy"):
+            np.testing.assert_array_equal(np.load(mine.open(name)), np.load(ref.open(name)))
+    assert find_unique_path(path) == str(tmp_path / "out.000.flow.zip")
+    open(tmp_path / "out.000.flow.zip", "w").close()
+    assert find_unique_path(str(tmp_path / "out.000.flow.zip")) == str(tmp_path / "out.001.flow.zip")
 
 
 def test_horn_schunck_own_blur_matches_cv2_blur():

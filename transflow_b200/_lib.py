@@ -93,6 +93,8 @@ SIGNATURES = {
     "tf_flow_postprocess_ex": (_i, [_vp, C.POINTER(FlowOpStruct), _i, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "tf_flow_filters": (_i, [_vp, C.POINTER(FlowOpStruct), _i, _vp, _vp, _i, _i, _vp]),
     "tf_flow_convolve": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
+    "tf_flow_merge": (_i, [C.POINTER(_vp), _i, _i, _vp, _i, _i, _vp]),
+    "tf_flow_upscale": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "tf_device_malloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
     "tf_device_free": (_i, [_vp]),
     "tf_layer_create": (_i, [C.POINTER(_vp), _i, _i, C.POINTER(LayerConfigStruct)]),

@@ -384,3 +384,90 @@ extern "C" int tf_flow_postprocess(float* flow, const float* mask, int forward, 
                                    void* stream) {
     return tf_flow_postprocess_to(flow, mask, forward, owner, nullptr, height, width, stream);
 }
+
+// ------------------------------------------------------------------------------------------
+// Pipeline._update_flow (pipeline.py:492-507): merge of several flow sources (pipeline.py:149-158,
+// utils.py:359-381) and integer upscale (utils.py:417-418), float32 like NumPy evaluates them
+// ------------------------------------------------------------------------------------------
+struct MergeArgs {
+    const float* src[TF_MAX_MERGE_FLOWS];
+    int n;
+};
+
+__global__ void __launch_bounds__(256) k_flow_merge(const MergeArgs a, int mode, float* __restrict__ out, size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float v = __ldg(a.src[0] + i);
+    switch (mode) {
+        case TF_MERGE_FIRST: break;
+        case TF_MERGE_SUM:
+        case TF_MERGE_AVERAGE:
+            for (int k = 1; k < a.n; k++) v = __fadd_rn(v, __ldg(a.src[k] + i));
+            if (mode == TF_MERGE_AVERAGE) v = __fdiv_rn(v, (float)a.n);
+            break;
+        case TF_MERGE_DIFFERENCE: {  // flows[0] - sum(flows[1:]), Python's sum starts from the int 0
+            if (a.n > 1) {
+                float s = __ldg(a.src[1] + i);
+                for (int k = 2; k < a.n; k++) s = __fadd_rn(s, __ldg(a.src[k] + i));
+                v = __fsub_rn(v, s);
+            }
+            break;
+        }
+        case TF_MERGE_PRODUCT:
+            for (int k = 1; k < a.n; k++) v = __fmul_rn(v, __ldg(a.src[k] + i));
+            break;
+        case TF_MERGE_MASKBIN:  // utils.py:368-373: |f| > 0.2 -> 1 else 0 (0.2 is weak: compared as float32)
+            for (int k = 1; k < a.n; k++) v = __fmul_rn(v, fabsf(__ldg(a.src[k] + i)) > 0.2f ? 1.f : 0.f);
+            break;
+        case TF_MERGE_MASKLIN:
+            for (int k = 1; k < a.n; k++) v = __fmul_rn(v, fabsf(__ldg(a.src[k] + i)));
+            break;
+        case TF_MERGE_ABSMAX: {  // utils.py:376-381: two flows, argmax of |.| (first wins ties)
+            float o = __ldg(a.src[1] + i);
+            if (fabsf(o) > fabsf(v)) v = o;
+            break;
+        }
+    }
+    out[i] = v;
+}
+
+extern "C" int tf_flow_merge(const float* const* flows, int n, int mode, float* out, int height, int width, void* stream) {
+    TF_REQUIRE(flows && out, TF_ERR_INVALID_ARG, "tf_flow_merge: null argument");
+    TF_REQUIRE(n >= 1 && n <= TF_MAX_MERGE_FLOWS, TF_ERR_INVALID_ARG, "tf_flow_merge: %d flows (1..%d)", n,
+               TF_MAX_MERGE_FLOWS);
+    TF_REQUIRE(mode >= TF_MERGE_FIRST && mode <= TF_MERGE_ABSMAX, TF_ERR_INVALID_ARG, "tf_flow_merge: unknown mode %d", mode);
+    TF_REQUIRE(mode != TF_MERGE_ABSMAX || n == 2, TF_ERR_INVALID_ARG,
+               "absmax merges exactly two flows (utils.py:378 reshapes to (2, ...)), got %d", n);
+    TF_REQUIRE(height > 0 && width > 0, TF_ERR_SHAPE, "tf_flow_merge: bad shape %dx%d", height, width);
+    if (int e = require_sm100()) return e;
+    MergeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n;
+    for (int k = 0; k < n; k++) {
+        TF_REQUIRE(flows[k], TF_ERR_INVALID_ARG, "tf_flow_merge: flow %d is null", k);
+        a.src[k] = flows[k];
+    }
+    size_t count = (size_t)height * width * 2;
+    k_flow_merge<<<(unsigned)((count + 255) / 256), 256, 0, as_stream(stream)>>>(a, mode, out, count);
+    TF_LAUNCHED();
+    return TF_OK;
+}
+
+__global__ void __launch_bounds__(256) k_flow_upscale(const float2* __restrict__ in, float2* __restrict__ out, int h, int w,
+                                                      int wf, int hf) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;  // output coordinates
+    int y = blockIdx.y;
+    if (x >= w * wf) return;
+    float2 v = __ldg(in + (size_t)(y / hf) * w + x / wf);
+    out[(size_t)y * (w * wf) + x] = make_float2(__fmul_rn(v.x, (float)wf), __fmul_rn(v.y, (float)hf));
+}
+
+extern "C" int tf_flow_upscale(const float* flow, float* out, int height, int width, int wf, int hf, void* stream) {
+    TF_REQUIRE(flow && out && flow != out, TF_ERR_INVALID_ARG, "tf_flow_upscale: bad buffers");
+    TF_REQUIRE(height > 0 && width > 0 && wf >= 1 && hf >= 1, TF_ERR_SHAPE, "tf_flow_upscale: bad shape / factors");
+    if (int e = require_sm100()) return e;
+    k_flow_upscale<<<dim3(ceil_div(width * wf, 256), height * hf), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float2*>(flow), reinterpret_cast<float2*>(out), height, width, wf, hf);
+    TF_LAUNCHED();
+    return TF_OK;
+}

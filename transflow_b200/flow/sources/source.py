@@ -326,7 +326,8 @@ class FlowSource:
                       seek_ckpt=seek_ckpt, seek_time=seek_time, duration_time=duration_time, repeat=repeat,
                       lock_expr=lock_expr, lock_mode=lock_mode)
         if isinstance(path, str) and path.endswith(".flow.zip"):
-            raise NotImplementedError("flow archives (.flow.zip) are outside the accelerated path (SURVEY.md 8f-4)")
+            from .archive import ArchiveFlowSource
+            return ArchiveFlowSource.Builder(path, **common)
         if use_mvs:
             raise NotImplementedError("motion-vector flow sources have no arithmetic to accelerate (SURVEY.md #11)")
         from .cv import CvFlowConfig, CvFlowSource

@@ -234,3 +234,33 @@ class PostProcess:
         check(self.lib.tf_flow_postprocess_ex(ptr(flow), arr, n, ptr(mask), int(self.forward), ptr(self.owner),
                                               ptr(out), self.h, self.w, stream_ptr()))
         return flow if out is None else out
+
+
+MERGE_MODES = {"first": 0, "sum": 1, "average": 2, "difference": 3, "product": 4, "maskbin": 5, "masklin": 6,
+               "absmax": 7}
+
+
+def merge_flows(flows, mode: str, out: torch.Tensor | None = None) -> torch.Tensor:
+    """``Pipeline.FLOW_MERGING_FUNCTIONS[mode](flows)`` (pipeline.py:149-158) on device flows."""
+    if mode not in MERGE_MODES:
+        raise KeyError(mode)
+    flows = [_cuda(f, torch.float32, "flow") for f in flows]
+    if not flows:
+        raise ValueError("no flow to merge")
+    h, w = flows[0].shape[:2]
+    if any(tuple(f.shape) != (h, w, 2) for f in flows):
+        raise ValueError("flows to merge must share one shape (H, W, 2)")
+    if out is None:
+        out = torch.empty_like(flows[0])
+    arr = (C.c_void_p * len(flows))(*[f.data_ptr() for f in flows])
+    check(_lib.load().tf_flow_merge(arr, len(flows), MERGE_MODES[mode], ptr(out), h, w, stream_ptr()))
+    return out
+
+
+def upscale_flow(flow: torch.Tensor, wf: int, hf: int) -> torch.Tensor:
+    """``utils.upscale_array(flow, wf, hf)`` (utils.py:417-418) on a device flow."""
+    flow = _cuda(flow, torch.float32, "flow")
+    h, w = flow.shape[:2]
+    out = torch.empty((h * int(hf), w * int(wf), 2), dtype=torch.float32, device=flow.device)
+    check(_lib.load().tf_flow_upscale(ptr(flow), ptr(out), h, w, int(wf), int(hf), stream_ptr()))
+    return out

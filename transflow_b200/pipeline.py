@@ -51,6 +51,10 @@ class Config:
     output_path: object = None             # None | "dir/%d.png" | callable(frame_index, rgb ndarray)
     size: tuple | None = None
     seed: int | None = None
+    extra_flow_paths: list = field(default_factory=list)   # more flow sources, merged per frame (pipeline.py:328-334)
+    flows_merging_function: str = "first"                  # key of FLOW_MERGING_FUNCTIONS (pipeline.py:149-158)
+    export_flow: object = None                             # None | path of the ".flow.zip" to write (pipeline.py:363-377)
+    round_flow: bool = False                               # export rounded integer flows (pipeline.py:505)
 
     def __post_init__(self):
         self.seek_time = parse_timestamp(self.seek_time) or 0
@@ -142,6 +146,39 @@ class Pipeline:
         self.flow_source = self._flow_builder.__enter__()
         self.flow_source.output = "device"
         self.expected_length = self.flow_source.length
+        from . import ops
+        if c.flows_merging_function not in ops.MERGE_MODES:
+            raise ValueError(f"Unknown flows merging function {c.flows_merging_function}")
+        self._extra_builders, self.extra_flow_sources = [], []
+        for path in c.extra_flow_paths:        # extra sources take no mask / kernel / filters (pipeline.py:331)
+            builder = FlowSource.from_args(path, cv_config=c.cv_config, size=c.size, direction=c.direction,
+                                           seek_time=c.seek_time, duration_time=c.duration_time, repeat=c.repeat)
+            src = builder.__enter__()
+            src.output = "device"
+            self._extra_builders.append(builder)
+            self.extra_flow_sources.append(src)
+        self.flow_output = None
+        if c.export_flow:
+            from .output import NumpyOutput
+            fs = self.flow_source
+            self.flow_output = NumpyOutput(str(c.export_flow), replace=True)
+            self.flow_output.write_meta({"path": c.flow_path if isinstance(c.flow_path, str) else repr(c.flow_path),
+                                         "width": fs.width, "height": fs.height, "framerate": fs.framerate,
+                                         "direction": fs.direction.value, "seek_time": c.seek_time})
+
+    def _next_flow(self) -> torch.Tensor:
+        """``Pipeline._update_flow`` (pipeline.py:492-507): one flow per source, merged, upscaled, exported."""
+        from . import ops
+        flows = [next(self.flow_source)]
+        for src in self.extra_flow_sources:
+            flows.append(next(src))
+        flow = flows[0]
+        if len(flows) > 1 or self.config.flows_merging_function != "first":
+            flow = ops.merge_flows(flows, self.config.flows_merging_function)
+        flow = self._upscale(flow)
+        if self.flow_output is not None:
+            self.flow_output.write_array(torch.round(flow).to(torch.int64) if self.config.round_flow else flow)
+        return flow
 
     def _setup_pixmaps_and_compositor(self):
         fw, fh = self.flow_source.width, self.flow_source.height
@@ -184,8 +221,8 @@ class Pipeline:
         if wf == 1 and hf == 1:
             return flow
         # utils.upscale_array (utils.py:417-418): vector scaling then block replicate
-        scaled = flow * torch.tensor([wf, hf], dtype=flow.dtype, device=flow.device)
-        return scaled.repeat_interleave(hf, dim=0).repeat_interleave(wf, dim=1).contiguous()
+        from . import ops
+        return ops.upscale_flow(flow, wf, hf)
 
     def _deliver(self, index: int, host: np.ndarray):
         out = self.config.output_path
@@ -262,10 +299,10 @@ class Pipeline:
                 if self.cancel_event is not None and self.cancel_event.is_set():
                     break
                 try:
-                    flow = next(self.flow_source)
+                    flow = self._next_flow()
                 except StopIteration:
                     break
-                frame = self.compositor.step(self._upscale(flow))
+                frame = self.compositor.step(flow)
                 self._emit(self.cursor, frame)
                 self.cursor += 1
                 if self.checkpoint_every is not None and self.cursor % self.checkpoint_every == 0:
@@ -290,6 +327,12 @@ class Pipeline:
         if self._flow_builder is not None:
             self._flow_builder.__exit__(None, None, None)
             self._flow_builder = None
+        for builder in getattr(self, "_extra_builders", []):
+            builder.__exit__(None, None, None)
+        self._extra_builders = []
+        if getattr(self, "flow_output", None) is not None:
+            self.flow_output.close()
+            self.flow_output = None
         for src in self._pixmaps:
             src.__exit__(None, None, None)
         self._pixmaps = []
