@@ -243,16 +243,35 @@ def run_ours(args):
     comp.set_sources({0: [PixmapSourceInterface(StillQueue(pix_dev), np.ones((H, W), bool))]})
     rgb = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
     gray = torch.empty((H, W), dtype=torch.uint8, device="cuda")
-    flow = torch.empty((H, W, 2), dtype=torch.float32, device="cuda")
+    # Two streams, like the reference's two processes (flow SourceProcess -> queue of 1 -> compositor main loop,
+    # pipeline.py:326-327): pair t+1 is estimated on the flow stream while the caller's stream post-processes and
+    # composites pair t.  Flow buffers ping-pong; events order producer and consumer.
+    pipelined = os.environ.get("TFB200_BENCH_STREAMS", "2") != "1"
+    flows = [torch.empty((H, W, 2), dtype=torch.float32, device="cuda") for _ in range(2)]
+    flow_stream = torch.cuda.Stream() if pipelined else torch.cuda.current_stream()
+    ev_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
     fb.prepare(0, ops.gray_from_bgr(frames_dev[0], gray))
+    torch.cuda.synchronize()
     state = {"slot": 0}
 
     def step(t):
         cur = state["slot"] ^ 1
-        ops.gray_from_bgr(frames_dev[frame_order(t + 1, N_DISTINCT)], gray)
-        fb.step(cur, gray, state["slot"], cur, flow)  # prepare(cur) overlapped with solve(prev, cur): forward
-        post(flow)
-        comp.step(flow, rgb)
+        k = t & 1
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(flow_stream):
+            if pipelined:
+                flow_stream.wait_event(ev_free[k])      # the compositor is done with this buffer (two steps ago)
+            ops.gray_from_bgr(frames_dev[frame_order(t + 1, N_DISTINCT)], gray)
+            fb.step(cur, gray, state["slot"], cur, flows[k])  # prepare(cur) overlapped with solve(prev, cur): forward
+            if pipelined:
+                ev_ready[k].record(flow_stream)
+        if pipelined:
+            main.wait_event(ev_ready[k])
+        post(flows[k])
+        comp.step(flows[k], rgb)
+        if pipelined:
+            ev_free[k].record(main)
         state["slot"] = cur
 
     for t in range(args.warmup):

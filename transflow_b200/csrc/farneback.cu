@@ -866,6 +866,13 @@ static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int var
         } else if (variant == 3) {
             if (int e = fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st))
                 return e;
+        } else if (variant == 8) {
+            // default: the half-buffer kernel where a level fills the machine (>= 1 Mpx: 168 vs 185 us at 4K, 47 vs
+            // 52 us at 1080p), the rolling-tile kernel on the small levels (its 512-thread CTAs start faster)
+            const bool big = (size_t)L.w * L.h >= ((size_t)1 << 20);
+            int e = big ? fb_iterate_half<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, 6, st)
+                        : fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st);
+            if (e) return e;
         } else if (variant >= 4) {
             if (int e = fb_iterate_half<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest,
                                             variant, st))
@@ -885,7 +892,7 @@ extern "C" int tf_farneback_solve(tf_farneback* h, int slot_left, int slot_right
     TF_REQUIRE(h && flow, TF_ERR_INVALID_ARG, "tf_farneback_solve: null argument");
     TF_REQUIRE((slot_left == 0 || slot_left == 1) && (slot_right == 0 || slot_right == 1), TF_ERR_INVALID_ARG,
                "tf_farneback_solve: slots must be 0 or 1");
-    TF_REQUIRE(variant >= 0 && variant <= 7, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
+    TF_REQUIRE(variant >= 0 && variant <= 8, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
     TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_solve: flow must be 8-byte aligned");
     cudaStream_t st = as_stream(stream);
     float2* out = reinterpret_cast<float2*>(flow);
@@ -899,7 +906,7 @@ extern "C" int tf_farneback_step(tf_farneback* h, int new_slot, const uint8_t* g
     TF_REQUIRE((new_slot == 0 || new_slot == 1) && (slot_left == 0 || slot_left == 1) &&
                    (slot_right == 0 || slot_right == 1),
                TF_ERR_INVALID_ARG, "tf_farneback_step: slots must be 0 or 1");
-    TF_REQUIRE(variant >= 0 && variant <= 7, TF_ERR_INVALID_ARG, "tf_farneback_step: unknown variant %d", variant);
+    TF_REQUIRE(variant >= 0 && variant <= 8, TF_ERR_INVALID_ARG, "tf_farneback_step: unknown variant %d", variant);
     TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_step: flow must be 8-byte aligned");
     cudaStream_t st = as_stream(stream);
     if (!h->aux) {

@@ -256,19 +256,18 @@ __global__ void __launch_bounds__(NT, (FbhCfg<MR, TX, NT, WANT, VEC>::CTAS))
                             for (int k = 0; k < G::WIN; k++) acc += sp[c * G::CHS + k];
                             s5[c] = acc;
                         }
+                        float2 res[8];
 #pragma unroll
-                        for (int o = 0; o < 8; o += 2) {
+                        for (int o = 0; o < 8; o++) {
                             if (o > 0) {
 #pragma unroll
                                 for (int c = 0; c < 5; c++)
                                     s5[c] += sp[c * G::CHS + o + G::WIN - 1] - sp[c * G::CHS + o - 1];
                             }
-                            float2 u = fbh_solve(s5[0], s5[1], s5[2], s5[3], s5[4], reg);
-#pragma unroll
-                            for (int c = 0; c < 5; c++) s5[c] += sp[c * G::CHS + o + G::WIN] - sp[c * G::CHS + o];
-                            float2 v = fbh_solve(s5[0], s5[1], s5[2], s5[3], s5[4], reg);
-                            emit(o, u, v);
+                            res[o] = fbh_solve(s5[0], s5[1], s5[2], s5[3], s5[4], reg);
                         }
+#pragma unroll
+                        for (int o = 0; o < 8; o += 2) emit(o, res[o], res[o + 1]);
                     } else {  // 128-bit window reads, channel by channel
                         const float4* rp = reinterpret_cast<const float4*>(old_half + row * G::PITCH + seg * 8);
                         float sum[5][8];
@@ -316,25 +315,20 @@ static int fb_launch_half(const float* R0, const float* R1, const float2* in, fl
         TF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, NT, G::SMEM));
         if (resident < 1) return fail(TF_ERR_CUDA, "k_fb_iter_half<%d,%d> does not fit an SM", MR, TX);
     }
-    // Chunk height: a CTA costs about (rows + 2m) matrix rows (the vertical halo is paid once per chunk) and
-    // the CTAs resident on one SM share its throughput: whole waves while the grid fits the resident set,
-    // CTAs/SMs plus half a CTA of tail once the hardware scheduler can balance.
+    // Chunk height, from sweeps at the 4K pyramid's sizes (tools/fb_level_sweep.py): the kernel runs best with the
+    // grid at a whole number k of resident waves (CTAs of one wave are in step, their phases overlap best when a
+    // second wave interleaves) and chunks of roughly 100 rows (taller chunks amortise the 2m-row prologue, shorter
+    // ones balance the tail): 4K -> 20 chunks of 112 rows (2.03 waves), 1080p -> 20 chunks of 56 rows (1.01).
     int strips = ceil_div(w, TX);
     int sms = sm_count();
-    int rows = G::TY;
+    int rows;
     if (g_fbh_rows > 0) {
         rows = ceil_div(g_fbh_rows, G::TY) * G::TY;
     } else {
-        double best = 1e30;
-        for (int r = G::TY; r < h + G::TY; r += G::TY) {
-            int ctas = strips * ceil_div(h, r);
-            double per_sm = ctas <= resident * sms ? (double)ceil_div(ctas, sms) : (double)ctas / sms + 0.5;
-            double cost = per_sm * (std::min(r, h) + 2 * MR);
-            if (cost < best) {
-                best = cost;
-                rows = r;
-            }
-        }
+        const double wave = (double)resident * sms;
+        int k = std::max(1, (int)lround((double)h * strips / (wave * 100.0)));
+        int chunks = std::max(1, (int)lround(k * wave / strips));
+        rows = std::max(G::TY, ceil_div(ceil_div(h, chunks), G::TY) * G::TY);
     }
     dim3 grid(strips, ceil_div(h, rows));
     float reg = (float)(1e-3 / (scale * scale));
@@ -345,7 +339,7 @@ static int fb_launch_half(const float* R0, const float* R1, const float2* in, fl
 }
 
 // variant 4: scalar B / C, 4 CTAs / SM (64 registers); 5: vector B / C, 3 CTAs / SM (80 registers);
-// 6: vector B / C, 4 CTAs / SM; 7: scalar B / C, 3 CTAs / SM.
+// 6: vector B / C, 4 CTAs / SM (the configuration variant 8 uses); 7: scalar B / C, 3 CTAs / SM.
 // Window radii below 4 (tiles of fewer than 8 rows) stay on the rolling-tile kernel.
 template <typename RT>
 static int fb_iterate_half(tf_farneback* h, FbLevel& L, const RT* R0, const RT* R1, float2* final_buf,

@@ -12,9 +12,10 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 
 
-#: solve kernel variant used when none is requested: 0 fused streaming (float sums in smem),
-#: 1 unfused reference kernels, 2 fused streaming with double sums in smem
-DEFAULT_FB_VARIANT = 3
+#: solve kernel variant used when none is requested: 8 = half-buffer kernel on the large pyramid levels, rolling-tile
+#: kernel on the small ones; 3 rolling tile everywhere; 4-7 half-buffer configurations; 0 / 2 fused streaming
+#: (float / double sums in shared memory); 1 unfused reference kernels
+DEFAULT_FB_VARIANT = 8
 
 
 def _cuda(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
