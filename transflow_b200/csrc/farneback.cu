@@ -867,9 +867,9 @@ static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int var
             if (int e = fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st))
                 return e;
         } else if (variant == 8) {
-            // default: the half-buffer kernel where a level fills the machine (>= 1 Mpx: 168 vs 185 us at 4K, 47 vs
-            // 52 us at 1080p), the rolling-tile kernel on the small levels (its 512-thread CTAs start faster)
-            const bool big = (size_t)L.w * L.h >= ((size_t)1 << 20);
+            // default: the half-buffer kernel where a level gives it enough CTAs (168 vs 185 us at 4K, 47 vs 52 us at
+            // 1080p, 16.6 vs 18.6 us at 960x540), the rolling-tile kernel below (10.5 vs 10.9 us at 480x270)
+            const bool big = (size_t)L.w * L.h >= (size_t)400000;
             int e = big ? fb_iterate_half<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, 6, st)
                         : fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st);
             if (e) return e;

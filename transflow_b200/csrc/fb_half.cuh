@@ -338,7 +338,7 @@ static int fb_launch_half(const float* R0, const float* R1, const float2* in, fl
     return TF_OK;
 }
 
-// variant 4: scalar B / C, 4 CTAs / SM (64 registers); 5: vector B / C, 3 CTAs / SM (80 registers);
+// variant 4: scalar B / C, 4 CTAs / SM (64 registers); 5: 128-column strips, 512 threads, 2 CTAs / SM, vector B / C;
 // 6: vector B / C, 4 CTAs / SM (the configuration variant 8 uses); 7: scalar B / C, 3 CTAs / SM.
 // Window radii below 4 (tiles of fewer than 8 rows) stay on the rolling-tile kernel.
 template <typename RT>
@@ -363,7 +363,7 @@ static int fb_iterate_half(tf_farneback* h, FbLevel& L, const RT* R0, const RT* 
             switch (m) {
 #define TF_FBH(MR)                                                                                      \
     case MR:                                                                                            \
-        e = variant == 5   ? fb_launch_half<MR, 64, 256, 3, true>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)  \
+        e = variant == 5   ? fb_launch_half<MR, 128, 512, 2, true>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)  \
             : variant == 6 ? fb_launch_half<MR, 64, 256, 4, true>(R0f, R1f, in, dst, L.w, L.h, scale, c, st) \
             : variant == 7 ? fb_launch_half<MR, 64, 256, 3, false>(R0f, R1f, in, dst, L.w, L.h, scale, c, st) \
                            : fb_launch_half<MR, 64, 256, 4, false>(R0f, R1f, in, dst, L.w, L.h, scale, c, st); \
