@@ -226,6 +226,21 @@ def test_farneback_matches_cv2(shape, params, variant):
     assert mean <= 1e-3 and mx <= 2e-2, (mean, mx)
 
 
+@pytest.mark.parametrize("variant", [None, 6, 3])
+@pytest.mark.parametrize("shape", [(33, 47), (40, 35), (64, 1001), (129, 66), (15, 300)])
+def test_farneback_edge_sizes(shape, variant):
+    """Frames smaller than a tile, odd widths (scalar store paths, byte-wise pyramid staging), pyramids cropped
+    by cv2's 32-pixel rule, strips with a single partial tile."""
+    from transflow_b200 import ops
+    h, w = shape
+    g0, g1 = clip_pair(h, w, seed=4)
+    want = F.farneback(g0, g1)
+    got = ops.Farneback(h, w, variant=variant)(dev(g0), dev(g1)).cpu().numpy()
+    mean, mx = epe(got, want)
+    assert mean <= 0.01 and mx <= 0.1, (mean, mx)
+    assert mean <= 1e-3 and mx <= 2e-2, (mean, mx)
+
+
 def test_farneback_fp16_storage_within_tolerance():
     from transflow_b200 import ops
     h, w = 480, 854
