@@ -595,6 +595,7 @@ static int g_fb_two_pass = 0;  // tf_farneback_tune(1, ..): separate blur passes
 #include "fb_iter.cuh"
 #include "fb_tile.cuh"
 #include "fb_half.cuh"
+#include "fb_stage.cuh"
 
 int g_fbh_rows = 0;
 extern "C" int tf_farneback_tune(int key, int value) {
@@ -866,6 +867,11 @@ static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int var
         } else if (variant == 3) {
             if (int e = fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st))
                 return e;
+        } else if (variant == 9) {
+            const bool big = (size_t)L.w * L.h >= (size_t)400000;
+            int e = big ? fb_iterate_stage<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st)
+                        : fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st);
+            if (e) return e;
         } else if (variant == 8) {
             // default: the half-buffer kernel where a level gives it enough CTAs (168 vs 185 us at 4K, 47 vs 52 us at
             // 1080p, 16.6 vs 18.6 us at 960x540), the rolling-tile kernel below (10.5 vs 10.9 us at 480x270)
@@ -892,7 +898,7 @@ extern "C" int tf_farneback_solve(tf_farneback* h, int slot_left, int slot_right
     TF_REQUIRE(h && flow, TF_ERR_INVALID_ARG, "tf_farneback_solve: null argument");
     TF_REQUIRE((slot_left == 0 || slot_left == 1) && (slot_right == 0 || slot_right == 1), TF_ERR_INVALID_ARG,
                "tf_farneback_solve: slots must be 0 or 1");
-    TF_REQUIRE(variant >= 0 && variant <= 8, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
+    TF_REQUIRE(variant >= 0 && variant <= 9, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
     TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_solve: flow must be 8-byte aligned");
     cudaStream_t st = as_stream(stream);
     float2* out = reinterpret_cast<float2*>(flow);
@@ -906,7 +912,7 @@ extern "C" int tf_farneback_step(tf_farneback* h, int new_slot, const uint8_t* g
     TF_REQUIRE((new_slot == 0 || new_slot == 1) && (slot_left == 0 || slot_left == 1) &&
                    (slot_right == 0 || slot_right == 1),
                TF_ERR_INVALID_ARG, "tf_farneback_step: slots must be 0 or 1");
-    TF_REQUIRE(variant >= 0 && variant <= 8, TF_ERR_INVALID_ARG, "tf_farneback_step: unknown variant %d", variant);
+    TF_REQUIRE(variant >= 0 && variant <= 9, TF_ERR_INVALID_ARG, "tf_farneback_step: unknown variant %d", variant);
     TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_step: flow must be 8-byte aligned");
     cudaStream_t st = as_stream(stream);
     if (!h->aux) {

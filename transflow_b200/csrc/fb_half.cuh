@@ -102,6 +102,136 @@ __device__ __forceinline__ void fbh_matrix(const float* a, float2 f, int x, int 
     m[4] = r6 * r2 + r5 * r3;  // h(2)
 }
 
+// ---- phase B: vertical window sums of (old half ++ new half) into the old half ----
+template <typename G, int NT, bool VEC>
+__device__ __forceinline__ void fbh_phase_b(float* __restrict__ old_half, const float* __restrict__ new_half, int tid) {
+    if (VEC) {  // two columns per thread, 64-bit accesses
+        for (int item = tid; item < 5 * (G::COLS / 2); item += NT) {
+            int c = item / (G::COLS / 2), lx = 2 * (item - c * (G::COLS / 2));
+            float2* oc = reinterpret_cast<float2*>(old_half + c * G::CHS + lx);
+            const float2* nc = reinterpret_cast<const float2*>(new_half + c * G::CHS + lx);
+            float2 v[G::TY];
+#pragma unroll
+            for (int j = 0; j < G::TY; j++) v[j] = oc[j * (G::PITCH / 2)];
+#pragma unroll
+            for (int j = G::TY - 2; j >= 0; j--) {
+                v[j].x += v[j + 1].x;
+                v[j].y += v[j + 1].y;
+            }
+            float2 p = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < G::TY; j++) {
+                float2 nv = nc[j * (G::PITCH / 2)];
+                p = j == 0 ? nv : make_float2(p.x + nv.x, p.y + nv.y);
+                oc[j * (G::PITCH / 2)] = make_float2(v[j].x + p.x, v[j].y + p.y);
+            }
+        }
+    } else {
+        for (int item = tid; item < 5 * G::COLS; item += NT) {
+            int c = item / G::COLS, lx = item - c * G::COLS;
+            float* oc = old_half + c * G::CHS + lx;
+            const float* nc = new_half + c * G::CHS + lx;
+            float v[G::TY];
+#pragma unroll
+            for (int j = 0; j < G::TY; j++) v[j] = oc[j * G::PITCH];
+#pragma unroll
+            for (int j = G::TY - 2; j >= 0; j--) v[j] += v[j + 1];
+            float p = 0.f;
+#pragma unroll
+            for (int j = 0; j < G::TY; j++) {
+                float nv = nc[j * G::PITCH];
+                p = j == 0 ? nv : p + nv;
+                oc[j * G::PITCH] = v[j] + p;
+            }
+        }
+    }
+}
+
+// ---- phase C: horizontal window sums + 2x2 solve + store for the tile's nout rows ----
+template <typename G, int TX, int NT, bool VEC>
+__device__ __forceinline__ void fbh_phase_c(const float* __restrict__ old_half, float2* __restrict__ flow_out, int tid,
+                                            int x0, int ty, int nout, int w, int h, float reg, int clip) {
+    {
+        constexpr int NSEG = TX / 8;
+        constexpr int WX = NSEG / 4;  // warp items per group of 8 rows
+        constexpr int NWI = ((G::TY + 7) / 8) * WX;
+        const int lane = tid & 31;
+        for (int wi = tid >> 5; wi < NWI; wi += NT / 32) {
+            const int seg = (lane & 3) + 4 * (wi % WX);
+            const int row = (lane >> 2) + 8 * (wi / WX);
+            if (row < nout) {
+                const int y = ty + row;
+                const int xg = x0 + seg * 8;
+                float2* dst = flow_out + (size_t)y * w + xg;
+                const bool wide = xg + 8 <= w && (w & 1) == 0;
+                // clip (last iteration only) and store outputs o, o + 1 of the segment
+                auto emit = [&](int o, float2 u, float2 v) {
+                    if (clip) {
+                        u.x = fminf(fmaxf(u.x, (float)(-(xg + o))), (float)(w - 1 - (xg + o)));
+                        u.y = fminf(fmaxf(u.y, (float)(-y)), (float)(h - 1 - y));
+                        v.x = fminf(fmaxf(v.x, (float)(-(xg + o + 1))), (float)(w - 2 - (xg + o)));
+                        v.y = fminf(fmaxf(v.y, (float)(-y)), (float)(h - 1 - y));
+                    }
+                    if (wide) {
+                        reinterpret_cast<float4*>(dst)[o >> 1] = make_float4(u.x, u.y, v.x, v.y);
+                    } else {
+                        if (xg + o < w) dst[o] = u;
+                        if (xg + o + 1 < w) dst[o + 1] = v;
+                    }
+                };
+                if (!VEC) {  // scalar sliding windows, all channels abreast
+                    const float* sp = old_half + row * G::PITCH + seg * 8;
+                    float s5[5];
+#pragma unroll
+                    for (int c = 0; c < 5; c++) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int k = 0; k < G::WIN; k++) acc += sp[c * G::CHS + k];
+                        s5[c] = acc;
+                    }
+                    float2 res[8];
+#pragma unroll
+                    for (int o = 0; o < 8; o++) {
+                        if (o > 0) {
+#pragma unroll
+                            for (int c = 0; c < 5; c++)
+                                s5[c] += sp[c * G::CHS + o + G::WIN - 1] - sp[c * G::CHS + o - 1];
+                        }
+                        res[o] = fbh_solve(s5[0], s5[1], s5[2], s5[3], s5[4], reg);
+                    }
+#pragma unroll
+                    for (int o = 0; o < 8; o += 2) emit(o, res[o], res[o + 1]);
+                } else {  // 128-bit window reads, channel by channel
+                    const float4* rp = reinterpret_cast<const float4*>(old_half + row * G::PITCH + seg * 8);
+                    float sum[5][8];
+#pragma unroll
+                    for (int c = 0; c < 5; c++) {
+                        float win[4 * G::NQ];
+#pragma unroll
+                        for (int k = 0; k < G::NQ; k++) {
+                            float4 t = rp[c * (G::CHS / 4) + k];
+                            win[4 * k] = t.x; win[4 * k + 1] = t.y; win[4 * k + 2] = t.z; win[4 * k + 3] = t.w;
+                        }
+                        float acc = 0.f;
+#pragma unroll
+                        for (int k = 0; k < G::WIN; k++) acc += win[k];
+                        sum[c][0] = acc;
+#pragma unroll
+                        for (int o = 1; o < 8; o++) {
+                            acc += win[o + G::WIN - 1] - win[o - 1];
+                            sum[c][o] = acc;
+                        }
+                    }
+#pragma unroll
+                    for (int o = 0; o < 8; o += 2)
+                        emit(o, fbh_solve(sum[0][o], sum[1][o], sum[2][o], sum[3][o], sum[4][o], reg),
+                             fbh_solve(sum[0][o + 1], sum[1][o + 1], sum[2][o + 1], sum[3][o + 1], sum[4][o + 1], reg));
+                }
+            }
+        }
+    }
+}
+
 template <int MR, int TX, int NT, int WANT, bool VEC>
 struct FbhCfg {
     using G = FbhGeom<MR, TX, VEC>;
@@ -175,128 +305,9 @@ __global__ void __launch_bounds__(NT, (FbhCfg<MR, TX, NT, WANT, VEC>::CTAS))
         const int ty = y0 + (hh - 1) * G::TY;
         const int nout = min(G::TY, y1 - ty);
         __syncthreads();
-        // ---- phase B: vertical window sums into the old half ----
-        if (VEC) {  // two columns per thread, 64-bit accesses
-            for (int item = tid; item < 5 * (G::COLS / 2); item += NT) {
-                int c = item / (G::COLS / 2), lx = 2 * (item - c * (G::COLS / 2));
-                float2* oc = reinterpret_cast<float2*>(old_half + c * G::CHS + lx);
-                const float2* nc = reinterpret_cast<const float2*>(new_half + c * G::CHS + lx);
-                float2 v[G::TY];
-#pragma unroll
-                for (int j = 0; j < G::TY; j++) v[j] = oc[j * (G::PITCH / 2)];
-#pragma unroll
-                for (int j = G::TY - 2; j >= 0; j--) {
-                    v[j].x += v[j + 1].x;
-                    v[j].y += v[j + 1].y;
-                }
-                float2 p = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int j = 0; j < G::TY; j++) {
-                    float2 nv = nc[j * (G::PITCH / 2)];
-                    p = j == 0 ? nv : make_float2(p.x + nv.x, p.y + nv.y);
-                    oc[j * (G::PITCH / 2)] = make_float2(v[j].x + p.x, v[j].y + p.y);
-                }
-            }
-        } else {
-            for (int item = tid; item < 5 * G::COLS; item += NT) {
-                int c = item / G::COLS, lx = item - c * G::COLS;
-                float* oc = old_half + c * G::CHS + lx;
-                const float* nc = new_half + c * G::CHS + lx;
-                float v[G::TY];
-#pragma unroll
-                for (int j = 0; j < G::TY; j++) v[j] = oc[j * G::PITCH];
-#pragma unroll
-                for (int j = G::TY - 2; j >= 0; j--) v[j] += v[j + 1];
-                float p = 0.f;
-#pragma unroll
-                for (int j = 0; j < G::TY; j++) {
-                    float nv = nc[j * G::PITCH];
-                    p = j == 0 ? nv : p + nv;
-                    oc[j * G::PITCH] = v[j] + p;
-                }
-            }
-        }
+        fbh_phase_b<G, NT, VEC>(old_half, new_half, tid);
         __syncthreads();
-        // ---- phase C: horizontal window sums + solve; lane = (4 segments) x (8 rows) ----
-        {
-            constexpr int NSEG = TX / 8;
-            constexpr int WX = NSEG / 4;  // warp items per group of 8 rows
-            constexpr int NWI = ((G::TY + 7) / 8) * WX;
-            const int lane = tid & 31;
-            for (int wi = tid >> 5; wi < NWI; wi += NT / 32) {
-                const int seg = (lane & 3) + 4 * (wi % WX);
-                const int row = (lane >> 2) + 8 * (wi / WX);
-                if (row < nout) {
-                    const int y = ty + row;
-                    const int xg = x0 + seg * 8;
-                    float2* dst = flow_out + (size_t)y * w + xg;
-                    const bool wide = xg + 8 <= w && (w & 1) == 0;
-                    // clip (last iteration only) and store outputs o, o + 1 of the segment
-                    auto emit = [&](int o, float2 u, float2 v) {
-                        if (clip) {
-                            u.x = fminf(fmaxf(u.x, (float)(-(xg + o))), (float)(w - 1 - (xg + o)));
-                            u.y = fminf(fmaxf(u.y, (float)(-y)), (float)(h - 1 - y));
-                            v.x = fminf(fmaxf(v.x, (float)(-(xg + o + 1))), (float)(w - 2 - (xg + o)));
-                            v.y = fminf(fmaxf(v.y, (float)(-y)), (float)(h - 1 - y));
-                        }
-                        if (wide) {
-                            reinterpret_cast<float4*>(dst)[o >> 1] = make_float4(u.x, u.y, v.x, v.y);
-                        } else {
-                            if (xg + o < w) dst[o] = u;
-                            if (xg + o + 1 < w) dst[o + 1] = v;
-                        }
-                    };
-                    if (!VEC) {  // scalar sliding windows, all channels abreast
-                        const float* sp = old_half + row * G::PITCH + seg * 8;
-                        float s5[5];
-#pragma unroll
-                        for (int c = 0; c < 5; c++) {
-                            float acc = 0.f;
-#pragma unroll
-                            for (int k = 0; k < G::WIN; k++) acc += sp[c * G::CHS + k];
-                            s5[c] = acc;
-                        }
-                        float2 res[8];
-#pragma unroll
-                        for (int o = 0; o < 8; o++) {
-                            if (o > 0) {
-#pragma unroll
-                                for (int c = 0; c < 5; c++)
-                                    s5[c] += sp[c * G::CHS + o + G::WIN - 1] - sp[c * G::CHS + o - 1];
-                            }
-                            res[o] = fbh_solve(s5[0], s5[1], s5[2], s5[3], s5[4], reg);
-                        }
-#pragma unroll
-                        for (int o = 0; o < 8; o += 2) emit(o, res[o], res[o + 1]);
-                    } else {  // 128-bit window reads, channel by channel
-                        const float4* rp = reinterpret_cast<const float4*>(old_half + row * G::PITCH + seg * 8);
-                        float sum[5][8];
-#pragma unroll
-                        for (int c = 0; c < 5; c++) {
-                            float win[4 * G::NQ];
-#pragma unroll
-                            for (int k = 0; k < G::NQ; k++) {
-                                float4 t = rp[c * (G::CHS / 4) + k];
-                                win[4 * k] = t.x; win[4 * k + 1] = t.y; win[4 * k + 2] = t.z; win[4 * k + 3] = t.w;
-                            }
-                            float acc = 0.f;
-#pragma unroll
-                            for (int k = 0; k < G::WIN; k++) acc += win[k];
-                            sum[c][0] = acc;
-#pragma unroll
-                            for (int o = 1; o < 8; o++) {
-                                acc += win[o + G::WIN - 1] - win[o - 1];
-                                sum[c][o] = acc;
-                            }
-                        }
-#pragma unroll
-                        for (int o = 0; o < 8; o += 2)
-                            emit(o, fbh_solve(sum[0][o], sum[1][o], sum[2][o], sum[3][o], sum[4][o], reg),
-                                 fbh_solve(sum[0][o + 1], sum[1][o + 1], sum[2][o + 1], sum[3][o + 1], sum[4][o + 1], reg));
-                    }
-                }
-            }
-        }
+        fbh_phase_c<G, TX, NT, VEC>(old_half, flow_out, tid, x0, ty, nout, w, h, reg, clip);
         __syncthreads();  // the next tile's phase A overwrites the half phase C just read
     }
 }
