@@ -522,21 +522,39 @@ __global__ void __launch_bounds__(256) k_fb_polyexp(const float* __restrict__ im
 // solve kernels (variant 1: materialised M / vertical sums)
 // ---------------------------------------------------------------------------------------------
 // resize(prevFlow, INTER_LINEAR) * (1 / pyr_scale)
+__device__ __forceinline__ float2 fb_upsample_one(const float2* __restrict__ r0, const float2* __restrict__ r1, int x0,
+                                                  int sw, float a, float b, float mul) {
+    int x1 = min(x0 + 1, sw - 1);
+    float2 p00 = __ldg(r0 + x0), p01 = __ldg(r0 + x1), p10 = __ldg(r1 + x0), p11 = __ldg(r1 + x1);
+    float r0x = p00.x * (1.f - a) + p01.x * a, r0y = p00.y * (1.f - a) + p01.y * a;
+    float r1x = p10.x * (1.f - a) + p11.x * a, r1y = p10.y * (1.f - a) + p11.y * a;
+    return make_float2((r0x * (1.f - b) + r1x * b) * mul, (r0y * (1.f - b) + r1y * b) * mul);
+}
+
+// two horizontally adjacent outputs per thread: one 128-bit store, tables read as 64-bit pairs
 __global__ void __launch_bounds__(256) k_fb_upsample_flow(const float2* __restrict__ src, float2* __restrict__ dst,
                                                           const int* __restrict__ sx, const float* __restrict__ tx,
                                                           const int* __restrict__ sy, const float* __restrict__ ty,
                                                           int sw, int sh, int w, int h, float mul) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int x = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     int y = blockIdx.y;
     if (x >= w) return;
-    int x0 = sx[x], y0 = sy[y];
-    int x1 = min(x0 + 1, sw - 1), y1 = min(y0 + 1, sh - 1);
-    float a = tx[x], b = ty[y];
-    float2 p00 = src[(size_t)y0 * sw + x0], p01 = src[(size_t)y0 * sw + x1];
-    float2 p10 = src[(size_t)y1 * sw + x0], p11 = src[(size_t)y1 * sw + x1];
-    float r0x = p00.x * (1.f - a) + p01.x * a, r0y = p00.y * (1.f - a) + p01.y * a;
-    float r1x = p10.x * (1.f - a) + p11.x * a, r1y = p10.y * (1.f - a) + p11.y * a;
-    dst[(size_t)y * w + x] = make_float2((r0x * (1.f - b) + r1x * b) * mul, (r0y * (1.f - b) + r1y * b) * mul);
+    int y0 = sy[y];
+    int y1 = min(y0 + 1, sh - 1);
+    float b = ty[y];
+    const float2* r0 = src + (size_t)y0 * sw;
+    const float2* r1 = src + (size_t)y1 * sw;
+    float2* out = dst + (size_t)y * w + x;
+    if (x + 1 < w && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        int2 xs = __ldg(reinterpret_cast<const int2*>(sx + x));
+        float2 ts = __ldg(reinterpret_cast<const float2*>(tx + x));
+        float2 u = fb_upsample_one(r0, r1, xs.x, sw, ts.x, b, mul);
+        float2 v = fb_upsample_one(r0, r1, xs.y, sw, ts.y, b, mul);
+        *reinterpret_cast<float4*>(out) = make_float4(u.x, u.y, v.x, v.y);
+    } else {
+        out[0] = fb_upsample_one(r0, r1, sx[x], sw, tx[x], b, mul);
+        if (x + 1 < w) out[1] = fb_upsample_one(r0, r1, sx[x + 1], sw, tx[x + 1], b, mul);
+    }
 }
 
 template <typename RT>
@@ -835,7 +853,7 @@ static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int var
         // where the initial flow of this level goes: the buffer iteration 0 reads from
         float2* init_buf = (variant == 1) ? final_buf : (((h->iterations - 1) & 1) ? final_buf : other_buf);
         if (prev) {
-            k_fb_upsample_flow<<<grid, 256, 0, st>>>(prev->flow, init_buf, L.fsx, L.ftx, L.fsy, L.fty, prev->w, prev->h,
+            k_fb_upsample_flow<<<dim3(ceil_div(ceil_div(L.w, 2), 256), L.h), 256, 0, st>>>(prev->flow, init_buf, L.fsx, L.ftx, L.fsy, L.fty, prev->w, prev->h,
                                                      L.w, L.h, (float)(1.0 / h->pyr_scale));
             TF_LAUNCHED();
         }
