@@ -355,7 +355,7 @@ __device__ __forceinline__ float fb_blur3(const uint8_t* __restrict__ gray, int 
 }
 
 template <int N, typename RT, bool FUSE3>
-__global__ void __launch_bounds__(256) k_fb_polyexp(const float* __restrict__ img, const uint8_t* __restrict__ gray,
+__global__ void __launch_bounds__(256, 5) k_fb_polyexp(const float* __restrict__ img, const uint8_t* __restrict__ gray,
                                                     float* __restrict__ img_out, RT* __restrict__ R, int w, int h,
                                                     PolyCoef pc, float k0, float k1) {
     constexpr int TX = 64, TY = 16, SW = TX + 2 * N, SH = TY + 2 * N, SP = SW + 1;

@@ -212,7 +212,7 @@ __device__ __forceinline__ long long lk_warp_sum(long long v) {
 }
 
 template <int KMAX>
-__global__ void __launch_bounds__(256) k_lk_track_warp(const uint8_t* __restrict__ I, const uint8_t* __restrict__ J,
+__global__ void __launch_bounds__(256, 4) k_lk_track_warp(const uint8_t* __restrict__ I, const uint8_t* __restrict__ J,
                                                        const short2* __restrict__ D, float2* __restrict__ next_pts,
                                                        int w, int h, int gw, int gh, int step, int win, int level,
                                                        int is_top) {
@@ -244,18 +244,17 @@ __global__ void __launch_bounds__(256) k_lk_track_warp(const uint8_t* __restrict
     // template of this lane's pixels + covariance of the interpolated derivatives
     int ival[KMAX];
     short2 dval[KMAX];
-    int wx[KMAX], wy[KMAX];
+    int woff[KMAX];  // window pixel as an offset y * w + x (x, y are re-derived on the rare border path)
     long long a11 = 0, a12 = 0, a22 = 0;
 #pragma unroll
     for (int k = 0; k < KMAX; k++) {
         int i = lane + 32 * k;
         ival[k] = 0;
         dval[k] = make_short2(0, 0);
-        wx[k] = wy[k] = 0;
+        woff[k] = 0;
         if (i < npx) {
             int y = i / win, x = i - y * win;
-            wx[k] = x;
-            wy[k] = y;
+            woff[k] = y * w + x;
             int X = ipx + x, Y = ipy + y;
             int i00 = lk_img(I, X, Y, w, h, insideI), i01 = lk_img(I, X + 1, Y, w, h, insideI);
             int i10 = lk_img(I, X, Y + 1, w, h, insideI), i11 = lk_img(I, X + 1, Y + 1, w, h, insideI);
@@ -288,12 +287,13 @@ __global__ void __launch_bounds__(256) k_lk_track_warp(const uint8_t* __restrict
 #pragma unroll
         for (int k = 0; k < KMAX; k++) {
             if (lane + 32 * k < npx) {
-                int X = inx + wx[k], Y = iny + wy[k];
                 int j00, j01, j10, j11;
                 if (insideJ) {
-                    const uint8_t* p = J + (size_t)Y * w + X;
+                    const uint8_t* p = J + ((size_t)iny * w + inx) + woff[k];
                     j00 = __ldg(p); j01 = __ldg(p + 1); j10 = __ldg(p + w); j11 = __ldg(p + w + 1);
                 } else {
+                    const int i = lane + 32 * k, wy = i / win, wx = i - wy * win;
+                    const int X = inx + wx, Y = iny + wy;
                     j00 = lk_img(J, X, Y, w, h, false); j01 = lk_img(J, X + 1, Y, w, h, false);
                     j10 = lk_img(J, X, Y + 1, w, h, false); j11 = lk_img(J, X + 1, Y + 1, w, h, false);
                 }
