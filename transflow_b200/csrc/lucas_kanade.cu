@@ -240,6 +240,8 @@ __global__ void __launch_bounds__(256, 4) k_lk_track_warp(const uint8_t* __restr
     const bool insideI = ipx >= 0 && ipy >= 0 && ipx + win < w && ipy + win < h;
     const int npx = win * win;
     const float FLT_SCALE = 1.f / (float)(1 << 20);
+    const float inv_win = 1.f / (float)win;
+    const bool unit = (q.w01 | q.w10 | q.w11) == 0;  // then w00 == 1 << LK_W_BITS: the template is the raw tap
 
     // template of this lane's pixels + covariance of the interpolated derivatives
     int ival[KMAX];
@@ -253,16 +255,36 @@ __global__ void __launch_bounds__(256, 4) k_lk_track_warp(const uint8_t* __restr
         dval[k] = make_short2(0, 0);
         woff[k] = 0;
         if (i < npx) {
-            int y = i / win, x = i - y * win;
+            // (i + 0.5) / win is at least 0.5 / win away from an integer: the float quotient truncates exactly
+            int y = __float2int_rz(((float)i + 0.5f) * inv_win), x = i - y * win;
             woff[k] = y * w + x;
             int X = ipx + x, Y = ipy + y;
-            int i00 = lk_img(I, X, Y, w, h, insideI), i01 = lk_img(I, X + 1, Y, w, h, insideI);
-            int i10 = lk_img(I, X, Y + 1, w, h, insideI), i11 = lk_img(I, X + 1, Y + 1, w, h, insideI);
-            short2 d00 = lk_der(D, X, Y, w, h, insideI), d01 = lk_der(D, X + 1, Y, w, h, insideI);
-            short2 d10 = lk_der(D, X, Y + 1, w, h, insideI), d11 = lk_der(D, X + 1, Y + 1, w, h, insideI);
-            ival[k] = lk_descale(i00 * q.w00 + i01 * q.w01 + i10 * q.w10 + i11 * q.w11, LK_W_BITS - 5);
-            int ixv = lk_descale(d00.x * q.w00 + d01.x * q.w01 + d10.x * q.w10 + d11.x * q.w11, LK_W_BITS);
-            int iyv = lk_descale(d00.y * q.w00 + d01.y * q.w01 + d10.y * q.w10 + d11.y * q.w11, LK_W_BITS);
+            int ixv, iyv;
+            if (insideI) {
+                // window inside the image (almost every point): no border logic; points on the integer grid
+                // (level 0 of a dense or strided grid) have weights (1, 0, 0, 0) and need one tap, not four
+                const size_t at = (size_t)Y * w + X;
+                if (unit) {
+                    ival[k] = (int)__ldg(I + at) << 5;
+                    short2 d = __ldg(D + at);
+                    ixv = d.x;
+                    iyv = d.y;
+                } else {
+                    int i00 = __ldg(I + at), i01 = __ldg(I + at + 1), i10 = __ldg(I + at + w), i11 = __ldg(I + at + w + 1);
+                    short2 d00 = __ldg(D + at), d01 = __ldg(D + at + 1), d10 = __ldg(D + at + w), d11 = __ldg(D + at + w + 1);
+                    ival[k] = lk_descale(i00 * q.w00 + i01 * q.w01 + i10 * q.w10 + i11 * q.w11, LK_W_BITS - 5);
+                    ixv = lk_descale(d00.x * q.w00 + d01.x * q.w01 + d10.x * q.w10 + d11.x * q.w11, LK_W_BITS);
+                    iyv = lk_descale(d00.y * q.w00 + d01.y * q.w01 + d10.y * q.w10 + d11.y * q.w11, LK_W_BITS);
+                }
+            } else {
+                int i00 = lk_img(I, X, Y, w, h, false), i01 = lk_img(I, X + 1, Y, w, h, false);
+                int i10 = lk_img(I, X, Y + 1, w, h, false), i11 = lk_img(I, X + 1, Y + 1, w, h, false);
+                short2 d00 = lk_der(D, X, Y, w, h, false), d01 = lk_der(D, X + 1, Y, w, h, false);
+                short2 d10 = lk_der(D, X, Y + 1, w, h, false), d11 = lk_der(D, X + 1, Y + 1, w, h, false);
+                ival[k] = lk_descale(i00 * q.w00 + i01 * q.w01 + i10 * q.w10 + i11 * q.w11, LK_W_BITS - 5);
+                ixv = lk_descale(d00.x * q.w00 + d01.x * q.w01 + d10.x * q.w10 + d11.x * q.w11, LK_W_BITS);
+                iyv = lk_descale(d00.y * q.w00 + d01.y * q.w01 + d10.y * q.w10 + d11.y * q.w11, LK_W_BITS);
+            }
             dval[k] = make_short2((short)ixv, (short)iyv);
             a11 += (long long)(ixv * ixv);
             a12 += (long long)(ixv * iyv);
@@ -292,7 +314,7 @@ __global__ void __launch_bounds__(256, 4) k_lk_track_warp(const uint8_t* __restr
                     const uint8_t* p = J + ((size_t)iny * w + inx) + woff[k];
                     j00 = __ldg(p); j01 = __ldg(p + 1); j10 = __ldg(p + w); j11 = __ldg(p + w + 1);
                 } else {
-                    const int i = lane + 32 * k, wy = i / win, wx = i - wy * win;
+                    const int i = lane + 32 * k, wy = __float2int_rz(((float)i + 0.5f) * inv_win), wx = i - wy * win;
                     const int X = inx + wx, Y = iny + wy;
                     j00 = lk_img(J, X, Y, w, h, false); j01 = lk_img(J, X + 1, Y, w, h, false);
                     j10 = lk_img(J, X, Y + 1, w, h, false); j11 = lk_img(J, X + 1, Y + 1, w, h, false);
