@@ -98,6 +98,9 @@ TF_API int tf_farneback_run(tf_farneback* h, const uint8_t* left, const uint8_t*
                      int variant, void* stream);
 TF_API int tf_farneback_num_levels(const tf_farneback* h);
 TF_API int tf_farneback_level_size(const tf_farneback* h, int level_index, int* width, int* height);
+/* Debug mode: prepare() also writes the finest level's blurred image, which otherwise only exists inside the
+ * fused polynomial-expansion kernel (needed by tf_farneback_debug_read(what = 0) on that level). */
+TF_API int tf_farneback_set_debug(tf_farneback* h, int on);
 /* Test hooks: copy stage outputs (as float32) to a device buffer.  what: 0 = pyramid image
  * (h, w); 1 = polynomial expansion (5, h, w) of `slot`; 2 = flow (h, w, 2) at the end of the
  * level during the last solve.  level_index 0 = coarsest. */

@@ -176,7 +176,7 @@ def test_farneback_stages_match_restatement(params):
     from transflow_b200 import ops
     h, w = 135, 201
     g0, g1 = clip_pair(h, w)
-    fb = ops.Farneback(h, w, **params)
+    fb = ops.Farneback(h, w, debug=True, **params)
     fb.prepare(0, dev(g0))
     plan = FB.level_plan(w, h, params.get("pyr_scale", 0.5), params.get("levels", 3))
     assert fb.level_sizes == [(l["h"], l["w"]) for l in plan]
@@ -196,7 +196,7 @@ def test_farneback_fused_pyramid_is_bit_identical_to_two_pass(shape, params):
     from transflow_b200 import ops, _lib
     h, w = shape
     g0, _ = clip_pair(h, w, seed=5)
-    fb = ops.Farneback(h, w, **params)
+    fb = ops.Farneback(h, w, debug=True, **params)
     lib = _lib.load()
     try:
         lib.tf_farneback_tune(1, 1)

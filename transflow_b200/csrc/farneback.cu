@@ -146,6 +146,7 @@ struct tf_farneback {
     int H, W;
     double pyr_scale;
     int levels_req, winsize, iterations, poly_n, flags, r_fp16;
+    int publish_finest;        // debug: also write the finest level's blurred image (fused into polyexp otherwise)
     double poly_sigma;
     PolyCoef pc;
     std::vector<FbLevel> lv;  // coarse -> fine
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(256, 5) k_fb_polyexp(const float* __restrict__
             for (int o = 0; o < 4; o++) {
                 if (lx + o < SW) {
                     float v = fmaf(k0, hz[2][o], fmaf(k1, hz[1][o], k0 * hz[0][o]));
-                    if (row_in && lx + o >= N && lx + o < N + TX)
+                    if (img_out && row_in && lx + o >= N && lx + o < N + TX)
                         img_out[(size_t)(y0 + ly - N) * w + (x0 + lx + o - N)] = v;
                     sI[ly * SP + lx + o] = v - c0i;
                 }
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(256, 5) k_fb_polyexp(const float* __restrict__
         if (FUSE3) {
             v = fb_blur3(gray, gx, gy, w, h, k0, k1);
             // interior of the tile: publish the pyramid image (debug hook / other consumers)
-            if (ly >= N && ly < N + TY && lx >= N && lx < N + TX && y0 + ly - N < h && x0 + lx - N < w)
+            if (img_out && ly >= N && ly < N + TY && lx >= N && lx < N + TX && y0 + ly - N < h && x0 + lx - N < w)
                 img_out[(size_t)gy * w + gx] = v;
         } else {
             v = __ldg(img + (size_t)gy * w + gx);
@@ -667,6 +668,7 @@ extern "C" int tf_farneback_create(tf_farneback** out, int height, int width, do
     h->H = height; h->W = width; h->pyr_scale = pyr_scale; h->levels_req = levels; h->winsize = winsize;
     h->iterations = iterations; h->poly_n = poly_n; h->poly_sigma = poly_sigma; h->flags = flags;
     h->r_fp16 = r_fp16 ? 1 : 0;
+    h->publish_finest = 0;
     h->T = h->M = nullptr;
     h->VS = nullptr;
     h->aux = nullptr;
@@ -736,6 +738,12 @@ extern "C" int tf_farneback_create(tf_farneback** out, int height, int width, do
     return TF_OK;
 }
 
+extern "C" int tf_farneback_set_debug(tf_farneback* h, int on) {
+    TF_REQUIRE(h, TF_ERR_INVALID_ARG, "tf_farneback_set_debug: null handle");
+    h->publish_finest = on != 0;
+    return TF_OK;
+}
+
 extern "C" int tf_farneback_num_levels(const tf_farneback* h) { return h ? (int)h->lv.size() : 0; }
 
 extern "C" int tf_farneback_level_size(const tf_farneback* h, int li, int* width, int* height) {
@@ -754,7 +762,8 @@ static int launch_polyexp(const tf_farneback* h, const FbLevel& L, int slot, con
 #define TF_PE(N)                                                                                              \
     case N:                                                                                               \
         if (gray_fused)                                                                                   \
-            k_fb_polyexp<N, RT, true><<<grid, 256, 0, st>>>(nullptr, gray_fused, L.img, R, L.w, L.h, h->pc, 0.25f, 0.5f); \
+            k_fb_polyexp<N, RT, true><<<grid, 256, 0, st>>>(nullptr, gray_fused, h->publish_finest ? L.img : nullptr, R, \
+                                                             L.w, L.h, h->pc, 0.25f, 0.5f);                      \
         else                                                                                              \
             k_fb_polyexp<N, RT, false><<<grid, 256, 0, st>>>(L.img, nullptr, nullptr, R, L.w, L.h, h->pc, 0.f, 0.f);  \
         break;
@@ -983,6 +992,9 @@ extern "C" int tf_farneback_debug_read(tf_farneback* h, int slot, int li, int wh
     FbLevel& L = h->lv[li];
     size_t n = (size_t)L.w * L.h;
     if (what == 0) {
+        bool fused = L.w == h->W && L.h == h->H && L.ksz == 3 && L.sigma <= 0;
+        TF_REQUIRE(!fused || h->publish_finest, TF_ERR_INVALID_ARG,
+                   "the finest level's image only exists after tf_farneback_set_debug(handle, 1) + prepare");
         TF_CUDA(cudaMemcpyAsync(out, L.img, n * 4, cudaMemcpyDeviceToDevice, st));
     } else if (what == 1) {
         unsigned blocks = (unsigned)((n + 255) / 256);

@@ -42,7 +42,7 @@ class Farneback:
     """Device Farneback flow with the parameters of ``CvFlowConfig.fb_*`` (cv.py:275-281)."""
 
     def __init__(self, height, width, pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5,
-                 poly_sigma=1.2, flags=0, r_fp16=None, variant=None):
+                 poly_sigma=1.2, flags=0, r_fp16=None, variant=None, debug=False):
         self.lib = _lib.load()
         self.h, self.w = int(height), int(width)
         if variant is None:
@@ -54,6 +54,8 @@ class Farneback:
         check(self.lib.tf_farneback_create(C.byref(self.handle), self.h, self.w, float(pyr_scale), int(levels),
                                            int(winsize), int(iterations), int(poly_n), float(poly_sigma),
                                            int(flags), int(bool(r_fp16))))
+        if debug:       # keep every pyramid image readable through debug_read
+            check(self.lib.tf_farneback_set_debug(self.handle, 1))
 
     def close(self):
         handle = getattr(self, "handle", None)
