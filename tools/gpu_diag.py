@@ -48,7 +48,7 @@ def main():
     plan = FB.level_plan(w, h, 0.5, 3)
     for variant in (1, 3, 0):
         try:
-            fb = ops.Farneback(h, w, variant=variant)
+            fb = ops.Farneback(h, w, variant=variant, debug=True)
             fb.prepare(0, dev(g0)); fb.prepare(1, dev(g1))
             for li, lvl in enumerate(plan):
                 k = lvl["k"]
