@@ -255,6 +255,26 @@ def test_farneback_staged_kernel_is_bit_identical_to_default():
         assert mean <= 0.01 and mx <= 0.1, (mean, mx)
 
 
+@pytest.mark.parametrize("shape,params", [((270, 484), dict()), ((540, 960), dict(poly_n=7, poly_sigma=1.5)),
+                                          ((200, 333), dict(poly_n=3, poly_sigma=0.9))])
+def test_farneback_folded_expansion_matches_two_stage(shape, params):
+    """Finest level: 3x3 blur folded into the expansion taps (default) vs blur then expansion (debug mode)."""
+    from transflow_b200 import ops
+    h, w = shape
+    g0, _ = clip_pair(h, w, seed=8)
+    plain = ops.Farneback(h, w, **params)
+    two = ops.Farneback(h, w, debug=True, **params)
+    plain.prepare(0, dev(g0))
+    two.prepare(0, dev(g0))
+    li = len(plain.level_sizes) - 1
+    a = plain.debug_read(0, li, 1).cpu().numpy()
+    b = two.debug_read(0, li, 1).cpu().numpy()
+    assert np.abs(a - b).max() < 2e-4, np.abs(a - b).max()
+    want = FB.poly_exp(FB.pyramid_image(g0, FB.level_plan(w, h, 0.5, 3)[li]), params.get("poly_n", 5),
+                       params.get("poly_sigma", 1.2)).transpose(2, 0, 1)
+    assert np.abs(a - want).max() < 2e-4, np.abs(a - want).max()
+
+
 def test_farneback_fp16_storage_within_tolerance():
     from transflow_b200 import ops
     h, w = 480, 854

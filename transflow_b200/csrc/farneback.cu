@@ -149,6 +149,7 @@ struct tf_farneback {
     int publish_finest;        // debug: also write the finest level's blurred image (fused into polyexp otherwise)
     double poly_sigma;
     PolyCoef pc;
+    PolyCoef pcf;              // pc convolved with the finest level's [1/4, 1/2, 1/4] blur (radius poly_n + 1)
     std::vector<FbLevel> lv;  // coarse -> fine
     float* T;                  // H x max(w) intermediate of the separable blur+resize
     float* M;                  // variant 1: 5 planes at the finest level
@@ -519,6 +520,142 @@ __global__ void __launch_bounds__(256, 5) k_fb_polyexp(const float* __restrict__
     }
 }
 
+// ---- polynomial expansion of the finest level with the 3x3 Gaussian FOLDED into the expansion filters ----------
+// R = PolyExp(Blur3(gray)) and every operator is linear and separable, so on tiles whose footprint lies inside the
+// frame the expansion taps are convolved with [1/4, 1/2, 1/4] once on the host (radius n + 1; symmetric taps stay
+// symmetric, the antisymmetric x*g taps stay antisymmetric) and the blurred image is never formed: no blur phase,
+// no second staging buffer.  Tiles touching the frame border keep the two-stage evaluation (reflected blur, then
+// replicated expansion borders).  Rounding differs from the two-stage form in the last bits only (1e-7 relative).
+template <int M, int SP, bool CENTER2>
+__device__ __forceinline__ void pe_vertical(const float* __restrict__ sI, float* __restrict__ sV, const PolyCoef& pc,
+                                            int tid) {
+    constexpr int TX = 64, TY = 16, SW = TX + 2 * M;
+    for (int i = tid; i < SW * (TY / 4); i += 256) {
+        int lx = i % SW, gy = (i / SW) * 4;
+        float win[4 + 2 * M];
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * M; j++) win[j] = sI[(gy + j) * SP + lx];
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            float r0 = win[o + M] * pc.g[0], r1 = 0.f, r2 = CENTER2 ? win[o + M] * pc.xxg[0] : 0.f;
+#pragma unroll
+            for (int k = 1; k <= M; k++) {
+                float up = win[o + M - k], dn = win[o + M + k];
+                float p = up + dn;
+                r0 = fmaf(pc.g[k], p, r0);
+                r1 = fmaf(pc.xg[k], dn - up, r1);
+                r2 = fmaf(pc.xxg[k], p, r2);
+            }
+            sV[(gy + o) * SP + lx] = r0;
+            sV[TY * SP + (gy + o) * SP + lx] = r1;
+            sV[2 * TY * SP + (gy + o) * SP + lx] = r2;
+        }
+    }
+}
+
+template <int M, int SP, bool CENTER2, typename RT>
+__device__ __forceinline__ void pe_horizontal(const float* __restrict__ sV, RT* __restrict__ R, const PolyCoef& pc, int tid,
+                                              int x0, int y0, int w, int h) {
+    constexpr int TX = 64, TY = 16;
+    // a warp covers 8 column groups x 4 rows: with the odd pitch the 32 lanes read 32 distinct banks
+    const int lane = tid & 31, wrp = tid >> 5;
+    const int ly = (lane >> 3) + 4 * (wrp >> 1), gx = ((lane & 7) + 8 * (wrp & 1)) * 4;
+    float w0[4 + 2 * M], w1[4 + 2 * M], w2[4 + 2 * M];
+#pragma unroll
+    for (int j = 0; j < 4 + 2 * M; j++) {
+        w0[j] = sV[ly * SP + gx + j];
+        w1[j] = sV[TY * SP + ly * SP + gx + j];
+        w2[j] = sV[2 * TY * SP + ly * SP + gx + j];
+    }
+    const int y = y0 + ly;
+    const size_t plane = (size_t)w * h;
+    float out[5][4];
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+        float b1 = w0[o + M] * pc.g[0], b2 = 0.f, b3 = w1[o + M] * pc.g[0], b5 = w2[o + M] * pc.g[0], b6 = 0.f;
+        float b4 = CENTER2 ? w0[o + M] * pc.xxg[0] : 0.f;
+#pragma unroll
+        for (int k = 1; k <= M; k++) {
+            float lo0 = w0[o + M - k], hi0 = w0[o + M + k];
+            float lo1 = w1[o + M - k], hi1 = w1[o + M + k];
+            float lo2 = w2[o + M - k], hi2 = w2[o + M + k];
+            float tg = hi0 + lo0;
+            b1 = fmaf(tg, pc.g[k], b1);
+            b4 = fmaf(tg, pc.xxg[k], b4);
+            b2 = fmaf(hi0 - lo0, pc.xg[k], b2);
+            b3 = fmaf(hi1 + lo1, pc.g[k], b3);
+            b6 = fmaf(hi1 - lo1, pc.xg[k], b6);
+            b5 = fmaf(hi2 + lo2, pc.g[k], b5);
+        }
+        out[0][o] = b3 * pc.ig11;                     // d/dy
+        out[1][o] = b2 * pc.ig11;                     // d/dx
+        out[2][o] = fmaf(b1, pc.ig03, b5 * pc.ig33);  // yy
+        out[3][o] = fmaf(b1, pc.ig03, b4 * pc.ig33);  // xx
+        out[4][o] = b6 * pc.ig55;                     // xy
+    }
+    const int x = x0 + gx;
+    if (y < h) {
+        size_t at = (size_t)y * w + x;
+#pragma unroll
+        for (int o = 0; o < 4; o++)
+            if (x + o < w) store_quad(R, at + o, make_float4(out[0][o], out[1][o], out[2][o], out[3][o]));
+        if (sizeof(RT) == 4 && x + 4 <= w && (w & 3) == 0) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(R) + 4 * plane + at) =
+                make_float4(out[4][0], out[4][1], out[4][2], out[4][3]);
+        } else {
+#pragma unroll
+            for (int o = 0; o < 4; o++)
+                if (x + o < w) store_c4(R, plane, at + o, out[4][o]);
+        }
+    }
+}
+
+// pc: expansion taps (radius N); pcf: the same taps convolved with [k0, k1, k0] (radius N + 1)
+template <int N, typename RT>
+__global__ void __launch_bounds__(256, 5) k_fb_polyexp_folded(const uint8_t* __restrict__ gray, RT* __restrict__ R, int w,
+                                                              int h, const PolyCoef pc, const PolyCoef pcf, float k0,
+                                                              float k1) {
+    constexpr int TX = 64, TY = 16, MF = N + 1, SP = TX + 2 * MF + 1;
+    __shared__ float sI[(TY + 2 * MF) * SP];
+    __shared__ float sV[3 * TY * SP];
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int tid = threadIdx.x;
+    const bool interior = MF <= 8 && x0 >= 8 && y0 - MF >= 0 && x0 + TX + 8 <= w && y0 + TY + MF <= h && (w & 3) == 0 &&
+                          (reinterpret_cast<uintptr_t>(gray) & 3) == 0;
+    if (interior) {
+        // gray footprint rows y0 - MF .. y0 + TY + MF - 1, columns x0 - MF .. x0 + TX + MF - 1, through aligned
+        // 32-bit loads of columns x0 - 8 .. x0 + TX + 7; the tile's first pixel is subtracted (see k_fb_polyexp)
+        constexpr int SH = TY + 2 * MF, GW = (TX + 16) / 4, SKIP = 8 - MF;
+        const float c0 = (float)__ldg(gray + (size_t)y0 * w + x0);
+        for (int i = tid; i < SH * GW; i += 256) {
+            int r = i / GW, q = i - r * GW;
+            uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(gray + (size_t)(y0 - MF + r) * w + (x0 - 8)) + q);
+            float* d = sI + r * SP + 4 * q - SKIP;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int lx = 4 * q + j - SKIP;
+                if (lx >= 0 && lx < TX + 2 * MF) d[j] = (float)((v >> (8 * j)) & 255u) - c0;
+            }
+        }
+        __syncthreads();
+        pe_vertical<MF, SP, true>(sI, sV, pcf, tid);
+        __syncthreads();
+        pe_horizontal<MF, SP, true, RT>(sV, R, pcf, tid, x0, y0, w, h);
+    } else {
+        constexpr int SW = TX + 2 * N, SH = TY + 2 * N;
+        const float c0 = fb_blur3(gray, min(x0, w - 1), min(y0, h - 1), w, h, k0, k1);
+        for (int i = tid; i < SH * SW; i += 256) {
+            int ly = i / SW, lx = i - ly * SW;
+            int gy = clampi(y0 + ly - N, 0, h - 1), gx = clampi(x0 + lx - N, 0, w - 1);
+            sI[ly * SP + lx] = fb_blur3(gray, gx, gy, w, h, k0, k1) - c0;
+        }
+        __syncthreads();
+        pe_vertical<N, SP, false>(sI, sV, pc, tid);
+        __syncthreads();
+        pe_horizontal<N, SP, false, RT>(sV, R, pc, tid, x0, y0, w, h);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // solve kernels (variant 1: materialised M / vertical sums)
 // ---------------------------------------------------------------------------------------------
@@ -674,6 +811,20 @@ extern "C" int tf_farneback_create(tf_farneback** out, int height, int width, do
     h->aux = nullptr;
     h->ev_start = nullptr;
     prepare_poly(poly_n, poly_sigma, h->pc);
+    {
+        // fold [k0, k1, k0] = [1/4, 1/2, 1/4] into the taps: c[k] = k0 t[k-1] + k1 t[k] + k0 t[k+1], t even or odd in k
+        const PolyCoef& a = h->pc;
+        PolyCoef& f = h->pcf;
+        f = a;
+        f.n = poly_n + 1;
+        auto even = [&](const float* t, int k) { int m = abs(k); return m <= poly_n ? (double)t[m] : 0.0; };
+        auto odd = [&](const float* t, int k) { int m = abs(k); return m <= poly_n ? (k < 0 ? -(double)t[m] : (double)t[m]) : 0.0; };
+        for (int k = 0; k <= poly_n + 1; k++) {
+            f.g[k] = (float)(0.25 * even(a.g, k - 1) + 0.5 * even(a.g, k) + 0.25 * even(a.g, k + 1));
+            f.xxg[k] = (float)(0.25 * even(a.xxg, k - 1) + 0.5 * even(a.xxg, k) + 0.25 * even(a.xxg, k + 1));
+            f.xg[k] = (float)(0.25 * odd(a.xg, k - 1) + 0.5 * odd(a.xg, k) + 0.25 * odd(a.xg, k + 1));
+        }
+    }
     // level crop (min_size 32) exactly as optflowgf.cpp
     int k = 0;
     double scale = 1;
@@ -761,7 +912,9 @@ static int launch_polyexp(const tf_farneback* h, const FbLevel& L, int slot, con
     switch (h->poly_n) {
 #define TF_PE(N)                                                                                              \
     case N:                                                                                               \
-        if (gray_fused)                                                                                   \
+        if (gray_fused && !h->publish_finest && !g_fb_two_pass)                                           \
+            k_fb_polyexp_folded<N, RT><<<grid, 256, 0, st>>>(gray_fused, R, L.w, L.h, h->pc, h->pcf, 0.25f, 0.5f); \
+        else if (gray_fused)                                                                              \
             k_fb_polyexp<N, RT, true><<<grid, 256, 0, st>>>(nullptr, gray_fused, h->publish_finest ? L.img : nullptr, R, \
                                                              L.w, L.h, h->pc, 0.25f, 0.5f);                      \
         else                                                                                              \

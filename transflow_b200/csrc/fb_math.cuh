@@ -9,7 +9,7 @@
 
 struct PolyCoef {
     int n;
-    float g[FB_MAX_POLY_N + 1], xg[FB_MAX_POLY_N + 1], xxg[FB_MAX_POLY_N + 1];  // taps k = 0..n
+    float g[FB_MAX_POLY_N + 2], xg[FB_MAX_POLY_N + 2], xxg[FB_MAX_POLY_N + 2];  // taps k = 0..n (n + 1 when folded)
     float ig11, ig03, ig33, ig55;
 };
 
