@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256) k_post_forward_scatter(const float2* __re
 
 // forward pass 2: flow := owner position - own position (0 where unclaimed); owner plane re-zeroed.
 __global__ void __launch_bounds__(256) k_post_forward_gather(float2* __restrict__ out, int* __restrict__ owner,
-                                                             int h, int w) {
+                                                             int h, int w, float inv_w) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;
     if (x >= w) return;
@@ -317,8 +317,14 @@ __global__ void __launch_bounds__(256) k_post_forward_gather(float2* __restrict_
     if (o != 0) {
         int s = o - 1;
         owner[p] = 0;
-        f.x = (float)(s % w - x);
-        f.y = (float)(s / w - y);
+        // s = sy * w + sx without an integer division: float estimate of the quotient (off by at most one: s < 2^30
+        // rounds to float within 2^-24 relative), corrected exactly in integers
+        int sy = __float2int_rz(__fmul_rn((float)s, inv_w));
+        int sx = s - sy * w;
+        if (sx < 0) { sy--; sx += w; }
+        if (sx >= w) { sy++; sx -= w; }
+        f.x = (float)(sx - x);
+        f.y = (float)(sy - y);
     }
     out[p] = f;  // already inside the frame: the final clip is the identity here
 }
@@ -343,7 +349,8 @@ extern "C" int tf_flow_postprocess_ex(float* flow, const tf_flow_op* ops, int n_
         k_post_forward_scatter<<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(flow), mask, owner, height, width,
                                                      packed);
         TF_LAUNCHED();
-        k_post_forward_gather<<<grid, 256, 0, st>>>(reinterpret_cast<float2*>(out), owner, height, width);
+        k_post_forward_gather<<<grid, 256, 0, st>>>(reinterpret_cast<float2*>(out), owner, height, width,
+                                                    1.0f / (float)width);
         TF_LAUNCHED();
     }
     return TF_OK;
