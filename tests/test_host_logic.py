@@ -1,0 +1,90 @@
+"""Host-side logic that needs no GPU: the video pixmap source (seek / repeat / length bookkeeping of
+``transflow/pixmap/cv.py``) checked against the REAL reference class where it is importable (the build container),
+and against the expected frame order everywhere."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+
+class HostCapture:
+    """cv2.VideoCapture stand-in over a (T, H, W, 3) BGR array (no torch / CUDA import)."""
+
+    def __init__(self, frames, fps=25.0):
+        self.frames, self.fps, self.pos = frames, float(fps), 0
+
+    def read(self):
+        if self.pos >= len(self.frames):
+            return False, None
+        self.pos += 1
+        return True, self.frames[self.pos - 1]
+
+    def get(self, prop):
+        import cv2
+        return {cv2.CAP_PROP_FRAME_WIDTH: self.frames.shape[2], cv2.CAP_PROP_FRAME_HEIGHT: self.frames.shape[1],
+                cv2.CAP_PROP_FPS: self.fps, cv2.CAP_PROP_FRAME_COUNT: len(self.frames)}.get(prop, 0)
+
+    def set(self, prop, value):
+        import cv2
+        if prop == cv2.CAP_PROP_POS_MSEC:
+            self.pos = int(round(value / 1000.0 * self.fps))
+        return True
+
+    def isOpened(self):
+        return True
+
+    def release(self):
+        pass
+
+
+def make_frames(n=5, h=6, w=8):
+    rng = np.random.default_rng(4)
+    return rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(seek=2), dict(repeat=3), dict(seek=1, repeat=2), dict(seek_time=0.08, repeat=2)])
+def test_video_pixmap_source_order_and_length(kw):
+    from transflow_b200.pixmap.cv import CvPixmapSource
+    frames = make_frames()
+    with CvPixmapSource(HostCapture(frames), **kw) as src:
+        assert (src.width, src.height, src.framerate) == (8, 6, 25)
+        got = list(src)
+        length = src.length
+    seek = kw.get("seek", int(kw["seek_time"] * 25) if "seek_time" in kw else 0)
+    one_pass = [f[:, :, ::-1] for f in frames[seek:]]
+    want = one_pass * kw.get("repeat", 1)
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a, b)
+    # the announced length only accounts for a TIME seek (pixmap/cv.py:39-44 of the reference)
+    assert length == (len(frames) - (seek if "seek_time" in kw else 0)) * kw.get("repeat", 1)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/transflow"), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("kw", [dict(), dict(seek=2, repeat=2), dict(seek_time=0.04, repeat=3)])
+def test_video_pixmap_source_matches_reference_class(kw, tmp_path):
+    """Same FFV1 clip through the reference's CvPixmapSource and ours: identical frames and metadata."""
+    import cv2
+    sys.path.insert(0, "/root/reference")
+    sys.dont_write_bytecode = True
+    try:
+        from transflow.pixmap.cv import CvPixmapSource as Ref
+    finally:
+        sys.path.remove("/root/reference")
+    from transflow_b200.pixmap.cv import CvPixmapSource
+    frames = make_frames(6, 32, 48)
+    path = str(tmp_path / "clip.avi")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"FFV1"), 25, (48, 32))
+    for f in frames:
+        vw.write(f)
+    vw.release()
+    with Ref(path, **kw) as ref:
+        want = [np.array(f) for f in ref]
+        meta = (ref.width, ref.height, ref.framerate, ref.length)
+    with CvPixmapSource(path, **kw) as src:
+        got = list(src)
+        assert (src.width, src.height, src.framerate, src.length) == meta
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a, b)

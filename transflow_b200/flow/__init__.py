@@ -1,4 +1,7 @@
+"""Flow plugin surface: ``FlowSource`` (``from_args`` -> ``Builder``) and its two enums, as ``transflow.flow`` exports
+them."""
 from .sources.source import FlowSource
 
-Direction = FlowSource.Direction
-LockMode = FlowSource.LockMode
+__all__ = ["FlowSource", "Direction", "LockMode"]
+
+Direction, LockMode = FlowSource.Direction, FlowSource.LockMode

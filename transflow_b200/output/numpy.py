@@ -1,4 +1,8 @@
-"""``.flow.zip`` writer (``transflow/output/numpy.py:6-15``): one ``NNNNNNNNN.npy`` per frame."""
+"""``.flow.zip`` writer: the interface of ``transflow/output/numpy.py`` (``NumpyOutput(path, replace)``,
+``write_array``), one ``%09d.npy`` member per flow.  Device flows are copied to the host here -- the one D2H copy
+of the export path."""
+import io
+
 import numpy as np
 
 from .zip import ZipOutput
@@ -7,12 +11,12 @@ from .zip import ZipOutput
 class NumpyOutput(ZipOutput):
 
     def __init__(self, path: str, replace: bool = False):
-        ZipOutput.__init__(self, path, replace)
+        super().__init__(path, replace)
         self.index = 0
 
     def write_array(self, array):
-        if hasattr(array, "is_cuda"):      # a device flow: one D2H copy at this legacy edge
-            array = array.cpu().numpy()
-        with self.archive.open(f"{self.index:09d}.npy", "w") as file:
-            np.save(file, array)
+        host = array.detach().cpu().numpy() if hasattr(array, "detach") else np.asarray(array)
+        payload = io.BytesIO()
+        np.save(payload, host, allow_pickle=False)
+        self.write_bytes(f"{self.index:09d}.npy", payload.getvalue())
         self.index += 1
