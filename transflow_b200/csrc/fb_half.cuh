@@ -46,6 +46,24 @@ __device__ __forceinline__ float2 fbh_solve(float s0, float s1, float s2, float 
     return make_float2(nx * r, ny * r);
 }
 
+// R0 and the flow are read once per CTA: keep them out of L1 so that the R1 taps (each used by ~4 neighbouring
+// pixels) stay resident.  g_fbh_stream (tf_farneback_tune key 2) switches the hint off for comparison.
+__device__ __forceinline__ float4 fbh_ld_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 fbh_ld_stream(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float fbh_ld_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // one row of bilinear taps: pixels (x1, y) and (x1 + 1, y) of R in the "4+1" layout
 struct FbhTaps {
     float4 q0, q1;
@@ -269,21 +287,14 @@ __global__ void __launch_bounds__(NT, (FbhCfg<MR, TX, NT, WANT, VEC>::CTAS))
             int r = rA;
             int gy_nx = clampi(gy_base + r, 0, h - 1);
             unsigned at = (unsigned)gy_nx * uw + (unsigned)gxA;
-            float2 f_nx = flow_in ? __ldg(flow_in + at) : make_float2(0.f, 0.f);
-            float4 q_nx = __ldg(R0q + at);
-            float e_nx = __ldg(R0e + at);
+            float2 f_nx = flow_in ? fbh_ld_stream(flow_in + at) : make_float2(0.f, 0.f);
+            float4 q_nx = fbh_ld_stream(R0q + at);
+            float e_nx = fbh_ld_stream(R0e + at);
 #pragma unroll 1
             for (; r < G::TY; r += S::NG) {
                 const float2 f = f_nx;
                 const float a[5] = {q_nx.x, q_nx.y, q_nx.z, q_nx.w, e_nx};
                 const int gy = gy_nx;
-                if (r + S::NG < G::TY) {
-                    gy_nx = clampi(gy_base + r + S::NG, 0, h - 1);
-                    at = (unsigned)gy_nx * uw + (unsigned)gxA;
-                    if (flow_in) f_nx = __ldg(flow_in + at);
-                    q_nx = __ldg(R0q + at);
-                    e_nx = __ldg(R0e + at);
-                }
                 // cvFloor; the float->int conversion saturates, so absurd displacements land outside the image
                 int x1 = __float2int_rd((float)gxA + f.x), yy1 = __float2int_rd((float)gy + f.y);
                 const bool in = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)yy1 < (unsigned)(h - 1);
@@ -292,6 +303,14 @@ __global__ void __launch_bounds__(NT, (FbhCfg<MR, TX, NT, WANT, VEC>::CTAS))
                     unsigned q = (unsigned)yy1 * uw + (unsigned)x1;
                     top = fbh_load_taps(R1q, R1e, q);
                     bot = fbh_load_taps(R1q, R1e, q + uw);
+                }
+                // next row's R0 / flow, requested after this row's gather (the gather is the load this row waits for)
+                if (r + S::NG < G::TY) {
+                    gy_nx = clampi(gy_base + r + S::NG, 0, h - 1);
+                    at = (unsigned)gy_nx * uw + (unsigned)gxA;
+                    if (flow_in) f_nx = fbh_ld_stream(flow_in + at);
+                    q_nx = fbh_ld_stream(R0q + at);
+                    e_nx = fbh_ld_stream(R0e + at);
                 }
                 float mm[5];
                 fbh_matrix(a, f, gxA, gy, w, h, in, top, bot, mm);
