@@ -72,8 +72,9 @@ TF_API int tf_farneback_create(tf_farneback** out, int height, int width, double
                         int winsize, int iterations, int poly_n, double poly_sigma, int flags,
                         int r_fp16);
 TF_API int tf_farneback_destroy(tf_farneback* h);
-/* Gaussian pyramid + polynomial expansion of one frame into slot 0 or 1 (cached across pairs,
- * since a frame is the right image of one pair and the left image of the next). */
+/* Gaussian pyramid + polynomial expansion of one frame into slot 0, 1 or 2 (cached across pairs,
+ * since a frame is the right image of one pair and the left image of the next; slot 2 is allocated
+ * on first use and only needed by tf_farneback_step_lane). */
 TF_API int tf_farneback_prepare(tf_farneback* h, int slot, const uint8_t* gray, void* stream);
 /* Coarse-to-fine displacement solve between two prepared slots -> flow (H, W, 2).
  * variant: 9 = experimental: half-buffer kernel with the R1 operand staged in shared memory by bulk copies
@@ -93,6 +94,15 @@ TF_API int tf_farneback_solve(tf_farneback* h, int slot_left, int slot_right, fl
  * and complete, from `stream`'s point of view, when the call's last kernel finishes. */
 TF_API int tf_farneback_step(tf_farneback* h, int new_slot, const uint8_t* gray, int slot_left, int slot_right,
                              float* flow, int variant, int clip, void* stream);
+/* tf_farneback_step on one of two solve LANES (0 or 1; lane 1's per-level flow buffers are allocated on
+ * first use).  Pair t's flow does not depend on pair t-1's (fb_flags == 0), so a streaming source can keep two
+ * pairs in flight: frame t lives in slot t % 3, pair (t, t+1) runs on lane t % 2 with its own `stream`, and
+ * every frame is still prepared exactly once.  The second pair fills the SMs the first leaves idle (the tails
+ * of its launches and the small pyramid levels): +9 % pairs/s at 4K on B200.  The handle orders, with events,
+ * (a) each solve after the expansion of BOTH its frames, whichever call built them, and (b) the overwrite of
+ * new_slot after every solve that read its previous frame, on either lane.  tf_farneback_step == lane 0. */
+TF_API int tf_farneback_step_lane(tf_farneback* h, int lane, int new_slot, const uint8_t* gray, int slot_left,
+                                  int slot_right, float* flow, int variant, int clip, void* stream);
 /* prepare(0, left) + prepare(1, right) + solve(0, 1). */
 TF_API int tf_farneback_run(tf_farneback* h, const uint8_t* left, const uint8_t* right, float* flow,
                      int variant, void* stream);

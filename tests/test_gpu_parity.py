@@ -161,6 +161,63 @@ def test_compositor_large_random_vs_oracle():
         np.testing.assert_array_equal(got, want)
 
 
+
+@pytest.mark.parametrize("direction", ["forward", "backward"])
+def test_farneback_two_pairs_in_flight_is_bit_identical(direction):
+    """tf_farneback_step_lane: frame t in slot t % 3, pair t on lane t % 2 on its own stream (what CvFlowSource and
+    bench.py do) must give exactly the flows of one pair at a time, for every frame of a longer clip, also when the
+    consumer is slow (the lanes run ahead) and when the source is rewound."""
+    from transflow_b200.flow import FlowSource
+    from transflow_b200.flow.sources.cv import ArrayCapture
+    from transflow_b200.synthetic import synthetic_clip
+    clip = synthetic_clip(270, 480, 11, seed=3)
+
+    def run(lanes, rewind_after=None):
+        out = []
+        with FlowSource.from_args(ArrayCapture(clip, 25.0), direction=direction) as src:
+            src.output = "device"
+            src.pairs_in_flight = lanes
+            for i, flow in enumerate(src):
+                out.append(flow.clone())
+                if i == 2:
+                    torch.cuda.synchronize()        # a slow consumer: both lanes finish and wait
+                if rewind_after is not None and i == rewind_after:
+                    break
+            if rewind_after is not None:
+                src.rewind()
+                src.output_frame_index = 0
+                out = [flow.clone() for flow in src]
+        torch.cuda.synchronize()
+        return [o.cpu().numpy() for o in out]
+
+    one = run(1)
+    two = run(2)
+    assert len(one) == len(two) == len(clip) - 1
+    for a, b in zip(one, two):
+        np.testing.assert_array_equal(a, b)
+    again = run(2, rewind_after=4)
+    assert len(again) == len(one)
+    for a, b in zip(one, again):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_farneback_step_lane_rejects_bad_arguments():
+    from transflow_b200 import ops
+    fb = ops.Farneback(64, 96)
+    g = torch.zeros((64, 96), dtype=torch.uint8, device="cuda")
+    fb.prepare(0, g)
+    with pytest.raises(ValueError):
+        fb.step(1, g, 0, 1, lane=2)             # no such lane
+    with pytest.raises(ValueError):
+        fb.step(3, g, 0, 3)                     # no such slot
+    with pytest.raises(ValueError):
+        fb.step(2, g, 0, 1)                     # the new frame is not part of the pair
+    with pytest.raises(ValueError):
+        fb.step(2, g, 1, 2)                     # slot 1 was never prepared
+    fb.step(1, g, 0, 1, lane=1)
+    torch.cuda.synchronize()
+
+
 # ------------------------------------------------------------------------------------------------
 FB_PARAMS = [dict(), dict(winsize=19, poly_n=7, poly_sigma=1.5), dict(pyr_scale=0.7, levels=4, iterations=2, poly_sigma=1.1)]
 

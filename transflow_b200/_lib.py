@@ -74,6 +74,7 @@ SIGNATURES = {
     "tf_farneback_prepare": (_i, [_vp, _i, _vp, _vp]),
     "tf_farneback_solve": (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),
     "tf_farneback_step": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
+    "tf_farneback_step_lane": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
     "tf_farneback_run": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "tf_farneback_num_levels": (_i, [_vp]),
     "tf_farneback_level_size": (_i, [_vp, _i, _pi, _pi]),

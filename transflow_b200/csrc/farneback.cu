@@ -122,6 +122,13 @@ static void prepare_poly(int n, double sigma, PolyCoef& pc) {
 // ---------------------------------------------------------------------------------------------
 // handle
 // ---------------------------------------------------------------------------------------------
+// Frame slots and solve lanes.  Slots 0 / 1 and lane 0 exist from tf_farneback_create; slot 2 and lane 1 are
+// allocated on first use (tf_farneback_step_lane): with three slots and two lanes, pair (t, t+1) can be solved on
+// one stream while pair (t+1, t+2) is solved on another and frame t+2's expansion is being built -- every frame is
+// still prepared exactly once.
+#define FB_SLOTS 3
+#define FB_LANES 2
+
 struct FbLevel {
     int k, w, h, ksz;
     double sigma;
@@ -133,9 +140,9 @@ struct FbLevel {
     int br_rows, br_pitch;  // fused blur+resize: largest footprint of a BR_TX x BR_TY tile (0 = use the two passes)
     size_t br_smem;
     float* img;     // pyramid image of the frame prepared last (h x w)
-    void* R[2];     // polynomial expansion per slot, 5*h*w elements (float or __half) in the "4+1" layout
-    float2* flow;   // per-level flow (the finest level writes into the caller's buffer)
-    float2* flow2;  // ping-pong partner for the fused iteration kernel
+    void* R[FB_SLOTS];        // polynomial expansion per slot, 5*h*w elements (float or __half) in the "4+1" layout
+    float2* flow[FB_LANES];   // per-level flow of a lane (the finest level writes into the caller's buffer)
+    float2* flow2[FB_LANES];  // ping-pong partner for the fused iteration kernel
     int* fsx;       // resize tables mapping the next-coarser level's flow onto this level
     float* ftx;
     int* fsy;
@@ -158,7 +165,9 @@ struct tf_farneback {
     // (coarse -> fine), while the caller's stream already solves the coarser levels
     cudaStream_t aux;
     cudaEvent_t ev_start;
-    std::vector<cudaEvent_t> ev_level;
+    std::vector<cudaEvent_t> ev_level[FB_SLOTS];  // per slot and level: that level's R of the slot's frame is built
+    cudaEvent_t ev_read[FB_SLOTS][FB_LANES];      // per slot and lane: the lane's last solve that read the slot is done
+    bool has_frame[FB_SLOTS];                     // a frame was prepared into the slot
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -775,13 +784,19 @@ extern "C" int tf_farneback_destroy(tf_farneback* h) {
     if (!h) return TF_OK;
     for (auto& l : h->lv) {
         cudaFree(l.gk); cudaFree(l.sx); cudaFree(l.tx); cudaFree(l.sy); cudaFree(l.ty);
-        cudaFree(l.img); cudaFree(l.R[0]); cudaFree(l.R[1]); cudaFree(l.flow); cudaFree(l.flow2);
+        cudaFree(l.img);
+        for (int i = 0; i < FB_SLOTS; i++) cudaFree(l.R[i]);
+        for (int i = 0; i < FB_LANES; i++) { cudaFree(l.flow[i]); cudaFree(l.flow2[i]); }
         cudaFree(l.fsx); cudaFree(l.ftx); cudaFree(l.fsy); cudaFree(l.fty);
     }
     cudaFree(h->T); cudaFree(h->M); cudaFree(h->VS);
     if (h->aux) cudaStreamDestroy(h->aux);
     if (h->ev_start) cudaEventDestroy(h->ev_start);
-    for (auto e : h->ev_level) cudaEventDestroy(e);
+    for (int i = 0; i < FB_SLOTS; i++) {
+        for (auto e : h->ev_level[i]) cudaEventDestroy(e);
+        for (int l = 0; l < FB_LANES; l++)
+            if (h->ev_read[i][l]) cudaEventDestroy(h->ev_read[i][l]);
+    }
     delete h;
     return TF_OK;
 }
@@ -810,6 +825,8 @@ extern "C" int tf_farneback_create(tf_farneback** out, int height, int width, do
     h->VS = nullptr;
     h->aux = nullptr;
     h->ev_start = nullptr;
+    memset(h->ev_read, 0, sizeof(h->ev_read));
+    memset(h->has_frame, 0, sizeof(h->has_frame));
     prepare_poly(poly_n, poly_sigma, h->pc);
     {
         // fold [k0, k1, k0] = [1/4, 1/2, 1/4] into the taps: c[k] = k0 t[k-1] + k1 t[k] + k0 t[k+1], t even or odd in k
@@ -869,8 +886,8 @@ extern "C" int tf_farneback_create(tf_farneback** out, int height, int width, do
         size_t n = (size_t)L.w * L.h;
         size_t rbytes = n * 5 * (h->r_fp16 ? 2 : 4);
         if (cudaMalloc(&L.img, n * 4) != cudaSuccess || cudaMalloc(&L.R[0], rbytes) != cudaSuccess ||
-            cudaMalloc(&L.R[1], rbytes) != cudaSuccess || cudaMalloc(&L.flow, n * 8) != cudaSuccess ||
-            cudaMalloc(&L.flow2, n * 8) != cudaSuccess)
+            cudaMalloc(&L.R[1], rbytes) != cudaSuccess || cudaMalloc(&L.flow[0], n * 8) != cudaSuccess ||
+            cudaMalloc(&L.flow2[0], n * 8) != cudaSuccess)
             return bail(fail(TF_ERR_CUDA, "cudaMalloc failed for pyramid level %d (%dx%d)", lvl, L.w, L.h));
         if (!h->lv.empty()) {
             const FbLevel& C = h->lv.back();  // next-coarser level
@@ -979,9 +996,34 @@ static int prepare_level(tf_farneback* h, FbLevel& L, int slot, const uint8_t* g
     return h->r_fp16 ? launch_polyexp<__half>(h, L, slot, g, st) : launch_polyexp<float>(h, L, slot, g, st);
 }
 
+// slot 2 / lane 1 are allocated on first use (cudaMalloc synchronises the device once)
+static int ensure_slot(tf_farneback* h, int slot) {
+    for (auto& L : h->lv)
+        if (!L.R[slot]) {
+            size_t rbytes = (size_t)L.w * L.h * 5 * (h->r_fp16 ? 2 : 4);
+            if (cudaMalloc(&L.R[slot], rbytes) != cudaSuccess)
+                return fail(TF_ERR_CUDA, "cudaMalloc failed for slot %d of a %dx%d level", slot, L.w, L.h);
+        }
+    return TF_OK;
+}
+
+static int ensure_lane(tf_farneback* h, int lane) {
+    for (auto& L : h->lv)
+        if (!L.flow[lane]) {
+            size_t n = (size_t)L.w * L.h;
+            if (cudaMalloc(&L.flow[lane], n * 8) != cudaSuccess || cudaMalloc(&L.flow2[lane], n * 8) != cudaSuccess)
+                return fail(TF_ERR_CUDA, "cudaMalloc failed for lane %d of a %dx%d level", lane, L.w, L.h);
+        }
+    return TF_OK;
+}
+
+static bool slot_ok(int s) { return s >= 0 && s < FB_SLOTS; }
+
 extern "C" int tf_farneback_prepare(tf_farneback* h, int slot, const uint8_t* gray, void* stream) {
     TF_REQUIRE(h && gray, TF_ERR_INVALID_ARG, "tf_farneback_prepare: null argument");
-    TF_REQUIRE(slot == 0 || slot == 1, TF_ERR_INVALID_ARG, "tf_farneback_prepare: slot must be 0 or 1");
+    TF_REQUIRE(slot_ok(slot), TF_ERR_INVALID_ARG, "tf_farneback_prepare: slot must be in [0, %d)", FB_SLOTS);
+    if (int e = ensure_slot(h, slot)) return e;
+    h->has_frame[slot] = true;
     cudaStream_t st = as_stream(stream);
     const bool batched = fused_blur_ok(h);
     if (batched)
@@ -993,7 +1035,7 @@ extern "C" int tf_farneback_prepare(tf_farneback* h, int slot, const uint8_t* gr
 
 template <typename RT>
 static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int variant, int clip, cudaStream_t st,
-                      bool wait_levels = false) {
+                      bool wait_levels = false, int lane = 0) {
     int m = h->winsize / 2;
     double scale = 1.0 / ((double)h->winsize * h->winsize);
     if (variant == 1 && !h->M) {
@@ -1005,9 +1047,12 @@ static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int var
     for (size_t li = 0; li < h->lv.size(); li++) {
         FbLevel& L = h->lv[li];
         bool finest = li + 1 == h->lv.size();
-        if (wait_levels) TF_CUDA(cudaStreamWaitEvent(st, h->ev_level[li], 0));  // this level's R of the new frame
-        float2* final_buf = finest ? flow_out : L.flow;
-        float2* other_buf = finest ? L.flow : L.flow2;
+        if (wait_levels) {  // this level's R of both frames (built on the auxiliary stream, maybe for the other lane)
+            TF_CUDA(cudaStreamWaitEvent(st, h->ev_level[sl][li], 0));
+            TF_CUDA(cudaStreamWaitEvent(st, h->ev_level[sr][li], 0));
+        }
+        float2* final_buf = finest ? flow_out : L.flow[lane];
+        float2* other_buf = finest ? L.flow[lane] : L.flow2[lane];
         const RT* R0 = reinterpret_cast<const RT*>(L.R[sl]);
         const RT* R1 = reinterpret_cast<const RT*>(L.R[sr]);
         dim3 grid(ceil_div(L.w, 256), L.h);
@@ -1015,7 +1060,7 @@ static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int var
         // where the initial flow of this level goes: the buffer iteration 0 reads from
         float2* init_buf = (variant == 1) ? final_buf : (((h->iterations - 1) & 1) ? final_buf : other_buf);
         if (prev) {
-            k_fb_upsample_flow<<<dim3(ceil_div(ceil_div(L.w, 2), 256), L.h), 256, 0, st>>>(prev->flow, init_buf, L.fsx, L.ftx, L.fsy, L.fty, prev->w, prev->h,
+            k_fb_upsample_flow<<<dim3(ceil_div(ceil_div(L.w, 2), 256), L.h), 256, 0, st>>>(prev->flow[lane], init_buf, L.fsx, L.ftx, L.fsy, L.fty, prev->w, prev->h,
                                                      L.w, L.h, (float)(1.0 / h->pyr_scale));
             TF_LAUNCHED();
         }
@@ -1076,8 +1121,8 @@ static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int var
 extern "C" int tf_farneback_solve(tf_farneback* h, int slot_left, int slot_right, float* flow, int variant, int clip,
                                   void* stream) {
     TF_REQUIRE(h && flow, TF_ERR_INVALID_ARG, "tf_farneback_solve: null argument");
-    TF_REQUIRE((slot_left == 0 || slot_left == 1) && (slot_right == 0 || slot_right == 1), TF_ERR_INVALID_ARG,
-               "tf_farneback_solve: slots must be 0 or 1");
+    TF_REQUIRE(slot_ok(slot_left) && slot_ok(slot_right) && h->has_frame[slot_left] && h->has_frame[slot_right],
+               TF_ERR_INVALID_ARG, "tf_farneback_solve: slots must be prepared slots in [0, %d)", FB_SLOTS);
     TF_REQUIRE(variant >= 0 && variant <= 9, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
     TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_solve: flow must be 8-byte aligned");
     cudaStream_t st = as_stream(stream);
@@ -1086,35 +1131,60 @@ extern "C" int tf_farneback_solve(tf_farneback* h, int slot_left, int slot_right
                      : solve_impl<float>(h, slot_left, slot_right, out, variant, clip, st);
 }
 
-extern "C" int tf_farneback_step(tf_farneback* h, int new_slot, const uint8_t* gray, int slot_left, int slot_right,
-                                 float* flow, int variant, int clip, void* stream) {
+extern "C" int tf_farneback_step_lane(tf_farneback* h, int lane, int new_slot, const uint8_t* gray, int slot_left,
+                                      int slot_right, float* flow, int variant, int clip, void* stream) {
     TF_REQUIRE(h && gray && flow, TF_ERR_INVALID_ARG, "tf_farneback_step: null argument");
-    TF_REQUIRE((new_slot == 0 || new_slot == 1) && (slot_left == 0 || slot_left == 1) &&
-                   (slot_right == 0 || slot_right == 1),
-               TF_ERR_INVALID_ARG, "tf_farneback_step: slots must be 0 or 1");
+    TF_REQUIRE(lane >= 0 && lane < FB_LANES, TF_ERR_INVALID_ARG, "tf_farneback_step: lane must be in [0, %d)", FB_LANES);
+    TF_REQUIRE(slot_ok(new_slot) && slot_ok(slot_left) && slot_ok(slot_right), TF_ERR_INVALID_ARG,
+               "tf_farneback_step: slots must be in [0, %d)", FB_SLOTS);
+    TF_REQUIRE((new_slot == slot_left) != (new_slot == slot_right), TF_ERR_INVALID_ARG,
+               "tf_farneback_step: the new frame must be exactly one side of the pair");
     TF_REQUIRE(variant >= 0 && variant <= 9, TF_ERR_INVALID_ARG, "tf_farneback_step: unknown variant %d", variant);
+    TF_REQUIRE(variant != 1 || lane == 0, TF_ERR_INVALID_ARG,
+               "tf_farneback_step: the unfused reference kernels (variant 1) share their scratch, lane 0 only");
     TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_step: flow must be 8-byte aligned");
+    const int old_slot = new_slot == slot_left ? slot_right : slot_left;
+    TF_REQUIRE(h->has_frame[old_slot], TF_ERR_INVALID_ARG, "tf_farneback_step: slot %d was never prepared", old_slot);
+    if (int e = ensure_slot(h, new_slot)) return e;
+    h->has_frame[new_slot] = true;
+    if (int e = ensure_lane(h, lane)) return e;
     cudaStream_t st = as_stream(stream);
     if (!h->aux) {
         TF_CUDA(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
         TF_CUDA(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
-        h->ev_level.resize(h->lv.size());
-        for (auto& e : h->ev_level) TF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (int s = 0; s < FB_SLOTS; s++) {
+            h->ev_level[s].resize(h->lv.size());
+            for (auto& e : h->ev_level[s]) TF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            for (int l = 0; l < FB_LANES; l++)
+                TF_CUDA(cudaEventCreateWithFlags(&h->ev_read[s][l], cudaEventDisableTiming));
+        }
     }
     // the auxiliary stream may overwrite new_slot only after everything already queued on the caller's
-    // stream (the previous pair's solve read that slot; `gray` was produced there) has finished
+    // stream (`gray` was produced there; this lane's earlier solves) and the other lanes' solves that read
+    // the slot have finished
     TF_CUDA(cudaEventRecord(h->ev_start, st));
     TF_CUDA(cudaStreamWaitEvent(h->aux, h->ev_start, 0));
+    for (int l = 0; l < FB_LANES; l++)
+        if (l != lane) TF_CUDA(cudaStreamWaitEvent(h->aux, h->ev_read[new_slot][l], 0));
     const bool batched = fused_blur_ok(h);
     if (batched)
         if (int e = blur_levels(h, gray, h->aux)) return e;
     for (size_t li = 0; li < h->lv.size(); li++) {
         if (int e = prepare_level(h, h->lv[li], new_slot, gray, h->aux, batched)) return e;
-        TF_CUDA(cudaEventRecord(h->ev_level[li], h->aux));
+        TF_CUDA(cudaEventRecord(h->ev_level[new_slot][li], h->aux));
     }
     float2* out = reinterpret_cast<float2*>(flow);
-    return h->r_fp16 ? solve_impl<__half>(h, slot_left, slot_right, out, variant, clip, st, true)
-                     : solve_impl<float>(h, slot_left, slot_right, out, variant, clip, st, true);
+    int e = h->r_fp16 ? solve_impl<__half>(h, slot_left, slot_right, out, variant, clip, st, true, lane)
+                      : solve_impl<float>(h, slot_left, slot_right, out, variant, clip, st, true, lane);
+    if (e) return e;
+    TF_CUDA(cudaEventRecord(h->ev_read[slot_left][lane], st));
+    TF_CUDA(cudaEventRecord(h->ev_read[slot_right][lane], st));
+    return TF_OK;
+}
+
+extern "C" int tf_farneback_step(tf_farneback* h, int new_slot, const uint8_t* gray, int slot_left, int slot_right,
+                                 float* flow, int variant, int clip, void* stream) {
+    return tf_farneback_step_lane(h, 0, new_slot, gray, slot_left, slot_right, flow, variant, clip, stream);
 }
 
 extern "C" int tf_farneback_run(tf_farneback* h, const uint8_t* left, const uint8_t* right, float* flow, int variant,
@@ -1140,7 +1210,7 @@ __global__ void __launch_bounds__(256) k_r_to_planes(const RT* __restrict__ R, f
 extern "C" int tf_farneback_debug_read(tf_farneback* h, int slot, int li, int what, float* out, void* stream) {
     TF_REQUIRE(h && out, TF_ERR_INVALID_ARG, "tf_farneback_debug_read: null argument");
     TF_REQUIRE(li >= 0 && li < (int)h->lv.size(), TF_ERR_INVALID_ARG, "tf_farneback_debug_read: bad level %d", li);
-    TF_REQUIRE(slot == 0 || slot == 1, TF_ERR_INVALID_ARG, "tf_farneback_debug_read: bad slot");
+    TF_REQUIRE(slot_ok(slot) && h->lv[li].R[slot], TF_ERR_INVALID_ARG, "tf_farneback_debug_read: bad slot");
     cudaStream_t st = as_stream(stream);
     FbLevel& L = h->lv[li];
     size_t n = (size_t)L.w * L.h;
@@ -1159,7 +1229,7 @@ extern "C" int tf_farneback_debug_read(tf_farneback* h, int slot, int li, int wh
     } else if (what == 2) {
         TF_REQUIRE(li + 1 < (int)h->lv.size(), TF_ERR_INVALID_ARG,
                    "tf_farneback_debug_read: the finest level's flow is the solve output");
-        TF_CUDA(cudaMemcpyAsync(out, L.flow, n * 8, cudaMemcpyDeviceToDevice, st));
+        TF_CUDA(cudaMemcpyAsync(out, L.flow[0], n * 8, cudaMemcpyDeviceToDevice, st));
     } else {
         return fail(TF_ERR_INVALID_ARG, "tf_farneback_debug_read: unknown selector %d", what);
     }

@@ -7,8 +7,10 @@ arithmetic step after the decode -- BGR->gray, Farneback / Horn-Schunck / Lucas-
 post-process -- runs in CUDA.  A frame's Farneback pyramid + polynomial expansion is computed
 once and reused as the other side of the next pair.
 """
+import collections
 import enum
 import json
+import os
 import re
 
 import numpy as np
@@ -169,6 +171,14 @@ class CvFlowSource(FlowSource):
         self._lookahead = None
         #: read one frame ahead so its H2D copy overlaps the current frame's kernels
         self.prefetch = True
+        #: Farneback pairs kept in flight (each on its own stream and handle lane).  The reference's flow process
+        #: also runs ahead of its consumer through a queue (pipeline.py:326); pair t does not depend on pair t-1
+        #: (fb_flags == 0), so the second pair fills the SMs the first leaves idle.  1 = strictly one pair at a time.
+        self.pairs_in_flight = int(os.environ.get("TFB200_FB_LANES", "2"))
+        self._inflight = collections.deque()
+        self._lane_streams = None
+        self._submitted = 0     # pairs submitted since the last (re)prepare; the previous frame is in slot _submitted % 3
+        self._eos = False
         self.config.start()
         FlowSource.__init__(self, *args, **kwargs)
 
@@ -274,8 +284,56 @@ class CvFlowSource(FlowSource):
         self.prev_gray = self._gray_on_device(frame)
         self._prepared = False
         self.prev_flow = None
+        self._drain()
+
+    def _drain(self):
+        for _, _, ev in self._inflight:
+            ev.synchronize()
+        self._inflight.clear()
+        self._submitted = 0
+        self._eos = False
+
+    def _next_farneback_lanes(self, engine, forward: bool) -> torch.Tensor:
+        """Farneback with up to two pairs in flight: frame t's expansion lives in slot t % 3, pair (t, t+1) is
+        solved on lane t % 2 / its own stream; flows are handed out in frame order."""
+        main = torch.cuda.current_stream()
+        if self._lane_streams is None:
+            self._lane_streams = [torch.cuda.Stream() for _ in range(2)]
+        if not self._prepared:
+            self._drain()
+            engine.prepare(0, self.prev_gray)
+            self._prepared = True
+            for s in self._lane_streams:
+                s.wait_stream(main)
+        while len(self._inflight) < self.pairs_in_flight and not self._eos:
+            success, frame = self._read_frame()
+            if frame is None or not success:
+                self._eos = True
+                break
+            n = self._submitted
+            lane, old, new = n & 1, n % 3, (n + 1) % 3
+            with torch.cuda.stream(self._lane_streams[lane]):
+                gray = self._gray_on_device(frame)
+                flow = (engine.step(new, gray, old, new, lane=lane) if forward
+                        else engine.step(new, gray, new, old, lane=lane))
+                ev = torch.cuda.Event()
+                ev.record()
+            self._inflight.append((flow, gray, ev))
+            self._submitted = n + 1
+        if not self._inflight:
+            raise StopIteration
+        flow, gray, ev = self._inflight.popleft()
+        main.wait_event(ev)
+        flow.record_stream(main)
+        self.prev_gray = gray
+        return flow
 
     def next(self) -> torch.Tensor:
+        if (self.config.method == CvFlowSource.Method.FARNEBACK and self.pairs_in_flight > 1
+                and self.prev_gray is not None
+                and self.direction in (FlowSource.Direction.FORWARD, FlowSource.Direction.BACKWARD)):
+            return self._next_farneback_lanes(self._method_engine(),
+                                              self.direction == FlowSource.Direction.FORWARD)
         success, frame = self._read_frame()
         if frame is None or not success:
             raise StopIteration
@@ -306,6 +364,7 @@ class CvFlowSource(FlowSource):
         return flow
 
     def close(self):
+        self._drain()
         self.capture.release()
         if self._engine is not None:
             self._engine.close()

@@ -82,12 +82,15 @@ class Farneback:
         return out
 
     def step(self, new_slot: int, gray: torch.Tensor, slot_left: int, slot_right: int, out=None,
-             clip=False) -> torch.Tensor:
-        """prepare(new_slot, gray) overlapped with solve(slot_left, slot_right) (streaming sources)."""
+             clip=False, lane: int = 0) -> torch.Tensor:
+        """prepare(new_slot, gray) overlapped with solve(slot_left, slot_right) (streaming sources).
+        ``lane`` (0 or 1) selects one of two sets of per-level flow buffers, so that two pairs can be in
+        flight on two streams (frame t in slot t % 3, pair t on lane t % 2)."""
         if out is None:
             out = torch.empty((self.h, self.w, 2), dtype=torch.float32, device="cuda")
-        check(self.lib.tf_farneback_step(self.handle, int(new_slot), ptr(self._gray(gray, "gray")), int(slot_left),
-                                         int(slot_right), ptr(out), self.variant, int(bool(clip)), stream_ptr()))
+        check(self.lib.tf_farneback_step_lane(self.handle, int(lane), int(new_slot), ptr(self._gray(gray, "gray")),
+                                              int(slot_left), int(slot_right), ptr(out), self.variant,
+                                              int(bool(clip)), stream_ptr()))
         return out
 
     def __call__(self, left: torch.Tensor, right: torch.Tensor, out=None) -> torch.Tensor:
