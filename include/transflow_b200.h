@@ -188,6 +188,13 @@ enum { TF_MERGE_FIRST = 0, TF_MERGE_SUM, TF_MERGE_AVERAGE, TF_MERGE_DIFFERENCE, 
 TF_API int tf_flow_merge(const float* const* flows, int n, int mode, float* out, int height, int width, void* stream);
 /* (H, W, 2) -> (H * hf, W * wf, 2): vectors scaled by (wf, hf), then block-replicated. */
 TF_API int tf_flow_upscale(const float* flow, float* out, int height, int width, int wf, int hf, void* stream);
+/* Flow visualisers of transflow/output/render.py:9-48 (pipeline.py:512-516, view_flow / view_flow_magnitude):
+ * mode 0 = render2d(flow (H, W, 2)) with 4 colours; mode 1 = render1d(|flow|) with the magnitude of
+ * pipeline.py:515 fused in, 2 colours; mode 2 = render1d(in (H, W)) for a scalar array.  `colors` is a HOST array
+ * of n_colors x 3 floats (R, G, B in 0..255).  float32 arithmetic in NumPy's evaluation order -> rgb u8 (H, W, 3),
+ * bit-exact with the reference. */
+TF_API int tf_flow_render(const float* in, int mode, float scale, const float* colors, int n_colors, int binary,
+                          uint8_t* rgb, int height, int width, void* stream);
 
 /* ---- compositor: transflow/compositor/** ---------------------------------------------------- */
 enum { TF_LAYER_MOVEREF = 0, TF_LAYER_SUM = 1, TF_LAYER_STATIC = 2, TF_LAYER_INTRODUCTION = 3 };

@@ -221,3 +221,51 @@ def merge_flows(flows, mode: str) -> np.ndarray:
 def upscale_array(arr: np.ndarray, wf: int, hf: int) -> np.ndarray:
     """``utils.upscale_array`` (``utils.py:417-418``)."""
     return np.kron(arr * (wf, hf), np.ones((hf, wf, 1))).astype(arr.dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# flow visualisers (transflow/output/render.py:9-48; called at pipeline.py:509-516)
+# ------------------------------------------------------------------------------------------------
+def _parse_color(string: str):
+    """``utils.parse_color`` (utils.py:316-324) for the forms the tests use (hex and rgb(...))."""
+    import re
+    m = re.match(r"^(?:rgb)?\((\d+), ?(\d+), ?(\d+)\)$", string, re.IGNORECASE)
+    if m:
+        return (int(m.group(1)), int(m.group(2)), int(m.group(3)))
+    x = int(string.replace("#", "").replace("0x", "").replace("x", ""), 16)
+    return ((x >> 16) & 255, (x >> 8) & 255, x & 255)
+
+
+def render1d(arr: np.ndarray, scale=1, colors=None, binary=False) -> np.ndarray:
+    """``render1d`` (render.py:9-28): two-colour ramp of a scalar array, float32 arithmetic."""
+    if colors is None:
+        colors = ("#000000", "#ffffff")
+    c = [np.array(_parse_color(s), dtype=np.float32) for s in colors]
+    shape = (*arr.shape[:2], 1)
+    if binary:
+        b = np.clip(np.round(scale * arr), 0, 1).reshape(shape)
+        a = 1 - b
+    else:
+        a = np.clip(1 - scale * arr, 0, 1).reshape(shape)
+        b = np.clip(scale * arr, 0, 1).reshape(shape)
+    frame = np.multiply(a, c[0]) + np.multiply(b, c[1])
+    return np.clip(frame, 0, 255).astype(np.uint8)
+
+
+def render2d(arr: np.ndarray, scale=1, colors=None) -> np.ndarray:
+    """``render2d`` (render.py:31-48): four-colour chart of a flow field."""
+    if colors is None:
+        colors = ("#ffff00", "#0000ff", "#ff00ff", "#00ff00")
+    c = [np.array(_parse_color(s), dtype=np.float32) for s in colors]
+    shape = (*arr.shape[:2], 1)
+    cy = np.clip(1 + scale * arr[:, :, 0], 0, 1).reshape(shape)
+    cb = np.clip(1 - scale * arr[:, :, 0], 0, 1).reshape(shape)
+    cm = np.clip(1 + scale * arr[:, :, 1], 0, 1).reshape(shape)
+    cg = np.clip(1 - scale * arr[:, :, 1], 0, 1).reshape(shape)
+    frame = .5 * (np.multiply(cy, c[0]) + np.multiply(cb, c[1]) + np.multiply(cm, c[2]) + np.multiply(cg, c[3]))
+    return np.clip(frame, 0, 255).astype(np.uint8)
+
+
+def flow_magnitude(flow: np.ndarray) -> np.ndarray:
+    """``numpy.sqrt(numpy.sum(numpy.power(flow, 2), axis=2))`` (pipeline.py:515)."""
+    return np.sqrt(np.sum(np.power(flow, 2), axis=2))

@@ -333,8 +333,40 @@ def merge_cases(tmp):
     print("merge cases:", len(out), "- reference read", len(back), "flows of our archive")
 
 
+RENDER_CASES = [
+    ("2d/default", dict(kind="2d", scale=1, colors=None)),
+    ("2d/scaled", dict(kind="2d", scale=0.37, colors=("#ff8000", "#0080ff", "rgb(12, 200, 77)", "#101010"))),
+    ("2d/strong", dict(kind="2d", scale=3, colors=None)),
+    ("1d/default", dict(kind="1d", scale=1, colors=None, binary=False)),
+    ("1d/scaled", dict(kind="1d", scale=0.21, colors=("#203040", "#f0e0d1"), binary=False)),
+    ("1d/binary", dict(kind="1d", scale=0.5, colors=("#ff0000", "#00ffff"), binary=True)),
+]
+
+
+def render_cases():
+    """The reference's flow visualisers ``render2d`` / ``render1d`` (``output/render.py``), the latter on the
+    magnitude exactly as ``Pipeline._update_output`` computes it (``pipeline.py:512-516``)."""
+    from transflow.output.render import render1d, render2d
+    rng = np.random.default_rng(23)
+    h, w = 37, 53
+    flow = (rng.standard_normal((h, w, 2)) * 2.5).astype(np.float32)
+    flow[0, :8] = np.array([[0, 0], [1, -1], [0.5, 0.5], [-0.5, 1.5], [2.5, -2.5], [1e-3, 0], [100, -100], [3, 4]],
+                           dtype=np.float32)
+    out = {"flow": flow}
+    for name, c in RENDER_CASES:
+        if c["kind"] == "2d":
+            out[name] = render2d(flow, c["scale"], c["colors"])
+        else:
+            mag = np.sqrt(np.sum(np.power(flow, 2), axis=2))
+            out[name] = render1d(mag, c["scale"], c["colors"], c["binary"])
+    np.savez_compressed(os.path.join(HERE, "render_golden.npz"), **out)
+    print("render cases:", len(RENDER_CASES))
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
+    if not only or "render" in only:
+        render_cases()
     with tempfile.TemporaryDirectory() as tmp:
         if not only or "compositor" in only:
             compositor_cases(tmp)

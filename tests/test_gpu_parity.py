@@ -703,6 +703,54 @@ def test_moveref_fast_path_equals_generic_kernel(reset, rgba_pixmap, tmp_path):
 
 
 # ------------------------------------------------------------------------------------------------
+# flow visualisers (output/render.py:9-48), bit-exact against frames the reference rendered
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["2d/default", "2d/scaled", "2d/strong", "1d/default", "1d/scaled", "1d/binary"])
+def test_render_matches_reference(name):
+    from tests.test_oracle import RENDER_CASES
+    from transflow_b200.output import render
+    z = G.load("render_golden.npz")
+    c = RENDER_CASES[name]
+    flow = dev(z["flow"])
+    if c["kind"] == "2d":
+        got = render.render2d(flow, c["scale"], c["colors"])
+    else:
+        got = render.render_magnitude(flow, c["scale"], c["colors"], c["binary"])
+        mag = dev(F.flow_magnitude(z["flow"]))
+        np.testing.assert_array_equal(render.render1d(mag, c["scale"], c["colors"], c["binary"]).cpu().numpy(), z[name])
+    assert got.dtype == torch.uint8 and tuple(got.shape) == z[name].shape
+    np.testing.assert_array_equal(got.cpu().numpy(), z[name])
+
+
+def test_render_full_size_vs_oracle_and_pipeline_view_flow():
+    """4K random flow against the oracle; the pipeline's view_flow / view_flow_magnitude outputs
+    (pipeline.py:509-516) equal the renderer applied to the flows the source yields."""
+    from transflow_b200.config import PixmapSourceConfig
+    from transflow_b200.flow import FlowSource
+    from transflow_b200.flow.sources.cv import ArrayCapture
+    from transflow_b200.output import render
+    from transflow_b200.pipeline import Config, Pipeline
+    from transflow_b200.synthetic import synthetic_clip
+    rng = np.random.default_rng(5)
+    flow = (rng.standard_normal((2160, 3840, 2)) * 3).astype(np.float32)
+    np.testing.assert_array_equal(render.render2d(dev(flow), 0.3).cpu().numpy(), F.render2d(flow, 0.3))
+    np.testing.assert_array_equal(render.render_magnitude(dev(flow), 0.3).cpu().numpy(),
+                                  F.render1d(F.flow_magnitude(flow), 0.3))
+    clip = synthetic_clip(96, 128, 5, seed=2)
+    for kw in (dict(view_flow=True, render_scale=0.25),
+               dict(view_flow_magnitude=True, render_scale=0.5, render_colors="#102030,#f0f0f0", render_binary=True)):
+        frames = {}
+        cfg = Config(ArrayCapture(clip), direction="backward", pixmap_sources=[PixmapSourceConfig("cnoise", layers=[0])],
+                     output_path=lambda i, rgb: frames.__setitem__(i, rgb.copy()), seed=1, **kw)
+        assert Pipeline(cfg).run() == len(clip) - 1
+        with FlowSource.from_args(ArrayCapture(clip), direction="backward") as src:
+            for i, fl in enumerate(src):
+                want = (F.render2d(fl, kw["render_scale"]) if "view_flow" in kw else
+                        F.render1d(F.flow_magnitude(fl), kw["render_scale"], ("#102030", "#f0f0f0"), True))
+                np.testing.assert_array_equal(frames[i], want)
+
+
+# ------------------------------------------------------------------------------------------------
 # float displacement map + bilinear remap (extension a16) against the NumPy restatement of the shaders
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("settings", ["floatmap", "floatmap:nearest", "floatmap:linear:decay=0.05:blur=3:scale=1.5"])

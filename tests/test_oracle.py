@@ -171,6 +171,30 @@ def test_merge_oracle_matches_reference(mode):
     np.testing.assert_array_equal(F.upscale_array(z["flow0"].copy(), 3, 2), z["upscale/3x2"])
 
 
+RENDER_CASES = {
+    "2d/default": dict(kind="2d", scale=1, colors=None),
+    "2d/scaled": dict(kind="2d", scale=0.37, colors=("#ff8000", "#0080ff", "rgb(12, 200, 77)", "#101010")),
+    "2d/strong": dict(kind="2d", scale=3, colors=None),
+    "1d/default": dict(kind="1d", scale=1, colors=None, binary=False),
+    "1d/scaled": dict(kind="1d", scale=0.21, colors=("#203040", "#f0e0d1"), binary=False),
+    "1d/binary": dict(kind="1d", scale=0.5, colors=("#ff0000", "#00ffff"), binary=True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(RENDER_CASES))
+def test_render_oracle_matches_reference(name):
+    """oracle render1d / render2d vs frames the reference's output/render.py produced (render_golden.npz)."""
+    from oracle import flow_cv as F
+    z = G.load("render_golden.npz")
+    c = RENDER_CASES[name]
+    if c["kind"] == "2d":
+        got = F.render2d(z["flow"], c["scale"], c["colors"])
+    else:
+        got = F.render1d(F.flow_magnitude(z["flow"]), c["scale"], c["colors"], c["binary"])
+    assert got.dtype == np.uint8
+    np.testing.assert_array_equal(got, z[name])
+
+
 def test_flow_archive_writer_matches_reference_format(tmp_path):
     """Our NumpyOutput writes what the reference's NumpyOutput wrote (tests/golden/ref_archive.flow.zip): same
     member names, same meta.json, identical arrays."""

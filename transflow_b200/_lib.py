@@ -97,6 +97,7 @@ SIGNATURES = {
     "tf_flow_convolve": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "tf_flow_merge": (_i, [C.POINTER(_vp), _i, _i, _vp, _i, _i, _vp]),
     "tf_flow_upscale": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "tf_flow_render": (_i, [_vp, _i, C.c_float, _vp, _i, _i, _vp, _i, _i, _vp]),
     "tf_device_malloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
     "tf_device_free": (_i, [_vp]),
     "tf_layer_create": (_i, [C.POINTER(_vp), _i, _i, C.POINTER(LayerConfigStruct)]),

@@ -478,3 +478,81 @@ extern "C" int tf_flow_upscale(const float* flow, float* out, int height, int wi
     TF_LAUNCHED();
     return TF_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Flow visualisers render2d / render1d (transflow/output/render.py:9-48, called at
+// pipeline.py:512-516 when view_flow / view_flow_magnitude is set): float32 arithmetic in NumPy's
+// evaluation order (no contraction), clip to [0, 255], truncating cast to uint8.
+//   mode 0  render2d(flow)                       4 colours (y, b, m, g)
+//   mode 1  render1d(sqrt(fx^2 + fy^2))          2 colours, the magnitude of pipeline.py:515 fused in
+//   mode 2  render1d(arr) for a scalar (H, W) array
+// ------------------------------------------------------------------------------------------
+struct RenderArgs {
+    float c[4][3];
+    float scale;
+    int mode, binary;
+};
+
+__device__ __forceinline__ float clip01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+
+__global__ void __launch_bounds__(256) k_flow_render(const float* __restrict__ in, uint8_t* __restrict__ rgb, size_t n,
+                                                     const RenderArgs a) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    float out[3];
+    if (a.mode == 0) {
+        float2 f = __ldg(reinterpret_cast<const float2*>(in) + p);
+        float sx = __fmul_rn(a.scale, f.x), sy = __fmul_rn(a.scale, f.y);
+        float cy = clip01(__fadd_rn(1.f, sx)), cb = clip01(__fsub_rn(1.f, sx));
+        float cm = clip01(__fadd_rn(1.f, sy)), cg = clip01(__fsub_rn(1.f, sy));
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float s = __fadd_rn(__fmul_rn(cy, a.c[0][k]), __fmul_rn(cb, a.c[1][k]));
+            s = __fadd_rn(s, __fmul_rn(cm, a.c[2][k]));
+            s = __fadd_rn(s, __fmul_rn(cg, a.c[3][k]));
+            out[k] = __fmul_rn(0.5f, s);
+        }
+    } else {
+        float v;
+        if (a.mode == 1) {
+            float2 f = __ldg(reinterpret_cast<const float2*>(in) + p);
+            v = __fsqrt_rn(__fadd_rn(__fmul_rn(f.x, f.x), __fmul_rn(f.y, f.y)));
+        } else {
+            v = __ldg(in + p);
+        }
+        float s = __fmul_rn(a.scale, v), ca, cb;
+        if (a.binary) {
+            cb = clip01(rintf(s));  // numpy.round: half to even
+            ca = __fsub_rn(1.f, cb);
+        } else {
+            ca = clip01(__fsub_rn(1.f, s));
+            cb = clip01(s);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) out[k] = __fadd_rn(__fmul_rn(ca, a.c[0][k]), __fmul_rn(cb, a.c[1][k]));
+    }
+    uint8_t* dst = rgb + 3 * p;
+#pragma unroll
+    for (int k = 0; k < 3; k++) dst[k] = (uint8_t)(int)fminf(fmaxf(out[k], 0.f), 255.f);
+}
+
+extern "C" int tf_flow_render(const float* in, int mode, float scale, const float* colors, int n_colors, int binary,
+                              uint8_t* rgb, int height, int width, void* stream) {
+    TF_REQUIRE(in && rgb && colors, TF_ERR_INVALID_ARG, "tf_flow_render: null argument");
+    TF_REQUIRE(mode >= 0 && mode <= 2, TF_ERR_INVALID_ARG, "tf_flow_render: unknown mode %d", mode);
+    TF_REQUIRE(n_colors == (mode == 0 ? 4 : 2), TF_ERR_INVALID_ARG, "tf_flow_render: mode %d takes %d colours, got %d",
+               mode, mode == 0 ? 4 : 2, n_colors);
+    TF_REQUIRE(height > 0 && width > 0, TF_ERR_SHAPE, "tf_flow_render: bad shape %dx%d", height, width);
+    if (int e = require_sm100()) return e;
+    RenderArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < n_colors; i++)
+        for (int k = 0; k < 3; k++) a.c[i][k] = colors[3 * i + k];
+    a.scale = scale;
+    a.mode = mode;
+    a.binary = binary != 0;
+    size_t n = (size_t)height * width;
+    k_flow_render<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(in, rgb, n, a);
+    TF_LAUNCHED();
+    return TF_OK;
+}

@@ -230,22 +230,35 @@ def bench_sharded(args, rank, world, local):
     def frame(idx):
         return feeder.get(idx) if io["host"] else frames_dev[B.frame_order(idx, B.N_DISTINCT)]
     fb = ops.Farneback(H, W)
-    post = ops.PostProcess(H, W, forward=True)
-    gray = torch.empty((H, W), dtype=torch.uint8, device="cuda")
+    # two pairs of a chunk in flight (handle lanes, tf_farneback_step_lane): pair i on lane i % 2 / its own stream,
+    # frame i in slot i % 3; each lane has its own post-process scratch.  Chunks stay ordered on the caller's stream.
+    lanes = max(1, min(2, int(os.environ.get("TFB200_FB_LANES", "2"))))
+    nslots = 3 if lanes > 1 else 2
+    posts = [ops.PostProcess(H, W, forward=True) for _ in range(lanes)]
+    grays = [torch.empty((H, W), dtype=torch.uint8, device="cuda") for _ in range(lanes)]
+    lane_streams = [torch.cuda.Stream() for _ in range(lanes)] if lanes > 1 else None
 
     def estimate_chunk(first_pair, n_pairs, outs=None):
         """K consecutive pairs: K + 1 prepares (one extra per chunk), K solves + post-processes.
         ``outs`` (raw device addresses, possibly peer memory) receive the post-processed flows."""
-        slot = 0
-        ops.gray_from_bgr(frame(first_pair), gray)
-        fb.prepare(slot, gray)
+        main = torch.cuda.current_stream()
+        ops.gray_from_bgr(frame(first_pair), grays[0])
+        fb.prepare(0, grays[0])
+        if lane_streams:
+            for s in lane_streams:
+                s.wait_stream(main)
         flows = []
         for i in range(n_pairs):
-            cur = slot ^ 1
-            ops.gray_from_bgr(frame(first_pair + i + 1), gray)
-            flow = fb.step(cur, gray, slot, cur)   # prepare(cur) overlapped with solve(prev, cur): forward
-            flows.append(post(flow, None if outs is None else outs[i]))
-            slot = cur
+            lane = i % lanes
+            with torch.cuda.stream(lane_streams[lane] if lane_streams else main):
+                old, new = i % nslots, (i + 1) % nslots
+                ops.gray_from_bgr(frame(first_pair + i + 1), grays[lane])
+                flow = fb.step(new, grays[lane], old, new, lane=lane)   # prepare(new) overlapped with solve: forward
+                flow.record_stream(main)
+                flows.append(posts[lane](flow, None if outs is None else outs[i]))
+        if lane_streams:
+            for s in lane_streams:
+                main.wait_stream(s)
         return flows
 
     comp = None

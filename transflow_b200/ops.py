@@ -270,3 +270,25 @@ def upscale_flow(flow: torch.Tensor, wf: int, hf: int) -> torch.Tensor:
     out = torch.empty((h * int(hf), w * int(wf), 2), dtype=torch.float32, device=flow.device)
     check(_lib.load().tf_flow_upscale(ptr(flow), ptr(out), h, w, int(wf), int(hf), stream_ptr()))
     return out
+
+
+RENDER_2D, RENDER_MAGNITUDE, RENDER_1D = 0, 1, 2
+
+
+def render_flow(arr: torch.Tensor, mode: int, scale: float, colors, binary: bool = False,
+                out: torch.Tensor | None = None) -> torch.Tensor:
+    """``render2d`` / ``render1d`` (output/render.py:9-48) on a device array -> uint8 (H, W, 3).
+    ``colors``: 4 (mode 0) or 2 (modes 1, 2) RGB triples in 0..255."""
+    arr = _cuda(arr, torch.float32, "arr")
+    want = 2 if mode in (RENDER_2D, RENDER_MAGNITUDE) else None
+    if (want and (arr.ndim != 3 or arr.shape[2] != 2)) or (not want and arr.ndim not in (2, 3)):
+        raise ValueError(f"render mode {mode}: unexpected array shape {tuple(arr.shape)}")
+    if not want and arr.ndim == 3 and arr.shape[2] != 1:
+        raise ValueError(f"render1d takes a scalar (H, W) array, got {tuple(arr.shape)}")
+    h, w = arr.shape[:2]
+    cols = (C.c_float * (3 * len(colors)))(*[float(v) for c in colors for v in c])
+    if out is None:
+        out = torch.empty((h, w, 3), dtype=torch.uint8, device=arr.device)
+    check(_lib.load().tf_flow_render(ptr(arr), int(mode), float(scale), cols, len(colors), int(bool(binary)), ptr(out),
+                                     h, w, stream_ptr()))
+    return out

@@ -55,12 +55,21 @@ class Config:
     flows_merging_function: str = "first"                  # key of FLOW_MERGING_FUNCTIONS (pipeline.py:149-158)
     export_flow: object = None                             # None | path of the ".flow.zip" to write (pipeline.py:363-377)
     round_flow: bool = False                               # export rounded integer flows (pipeline.py:505)
+    view_flow: bool = False                                # output render2d(flow) instead of the composite (pipeline.py:512)
+    view_flow_magnitude: bool = False                      # output render1d(|flow|) (pipeline.py:514-516)
+    render_scale: float = 1
+    render_colors: object = None                           # "c1,c2,..." | list | tuple | None (config.py:248-252)
+    render_binary: bool = False
 
     def __post_init__(self):
         self.seek_time = parse_timestamp(self.seek_time) or 0
         self.duration_time = parse_timestamp(self.duration_time)
         if self.compositor_background is None:
             self.compositor_background = "#FFFFFF"
+        if isinstance(self.render_colors, str):
+            self.render_colors = tuple(self.render_colors.split(","))
+        elif isinstance(self.render_colors, list):
+            self.render_colors = tuple(self.render_colors)
         if self.seed is None:
             self.seed = int.from_bytes(os.urandom(4), "little")
         known = {layer.index for layer in self.layers}
@@ -224,6 +233,18 @@ class Pipeline:
         from . import ops
         return ops.upscale_flow(flow, wf, hf)
 
+    def _output_frame(self, flow: torch.Tensor):
+        """``compositor.update(flow)`` then ``_update_output`` (pipeline.py:562-564, 509-521): the flow visualisers
+        replace the composite when asked for."""
+        c = self.config
+        if c.view_flow or c.view_flow_magnitude:
+            from .output import render
+            self.compositor.update(flow)
+            if c.view_flow:
+                return render.render2d(flow, c.render_scale, c.render_colors)
+            return render.render_magnitude(flow, c.render_scale, c.render_colors, c.render_binary)
+        return self.compositor.step(flow)
+
     def _deliver(self, index: int, host: np.ndarray):
         out = self.config.output_path
         if callable(out):
@@ -302,8 +323,9 @@ class Pipeline:
                     flow = self._next_flow()
                 except StopIteration:
                     break
-                frame = self.compositor.step(flow)
-                self._emit(self.cursor, frame)
+                frame = self._output_frame(flow)
+                if frame is not None:
+                    self._emit(self.cursor, frame)
                 self.cursor += 1
                 if self.checkpoint_every is not None and self.cursor % self.checkpoint_every == 0:
                     self.export_checkpoint()
