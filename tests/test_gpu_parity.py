@@ -298,15 +298,17 @@ def test_farneback_edge_sizes(shape, variant):
     assert mean <= 1e-3 and mx <= 2e-2, (mean, mx)
 
 
-def test_farneback_staged_kernel_is_bit_identical_to_default():
-    """Variant 9 (R1 box staged in shared memory by bulk copies + mbarrier, global fallback outside the box) runs the
-    same arithmetic as the default kernel: identical flows, also when the motion exceeds the staging margin."""
+@pytest.mark.parametrize("variant", [9, 10])
+def test_farneback_staged_kernel_is_bit_identical_to_default(variant):
+    """Variants 9 / 10 (R1 box staged in shared memory by bulk copies + mbarrier, global fallback outside the box; 64-
+    or 32-column strips) run the same arithmetic as the default kernel: identical flows, also when the motion
+    exceeds the staging margin."""
     from transflow_b200 import ops
     h, w = 540, 960
     g0, g1 = clip_pair(h, w, seed=6)
     for right in (g1, np.roll(g0, (9, 13), (0, 1))):
         want = ops.Farneback(h, w, variant=8)(dev(g0), dev(right)).cpu().numpy()
-        got = ops.Farneback(h, w, variant=9)(dev(g0), dev(right)).cpu().numpy()
+        got = ops.Farneback(h, w, variant=variant)(dev(g0), dev(right)).cpu().numpy()
         np.testing.assert_array_equal(got, want)
         mean, mx = epe(got, F.farneback(g0, right))
         assert mean <= 0.01 and mx <= 0.1, (mean, mx)

@@ -137,7 +137,8 @@ struct FbLevel {
     float* tx;
     int* sy;
     float* ty;
-    int br_rows, br_pitch;  // fused blur+resize: largest footprint of a BR_TX x BR_TY tile (0 = use the two passes)
+    int br_rows, br_pitch;  // fused blur+resize: largest footprint of a br_tw x br_th tile (0 = use the two passes)
+    int br_tw, br_th;       // tile of the fused blur+resize kernel (level pixels), a power of two wide
     size_t br_smem;
     float* img;     // pyramid image of the frame prepared last (h x w)
     void* R[FB_SLOTS];        // polynomial expansion per slot, 5*h*w elements (float or __half) in the "4+1" layout
@@ -228,6 +229,8 @@ __global__ void __launch_bounds__(256) k_fb_vpass(const float* __restrict__ T, f
 // with the SAME operation order as the two separate passes, so the result is bit-identical to them.
 #define BR_TX 32
 #define BR_TY 8
+#define BR_NT 256  // threads per block; tiles are BR_TX x BR_TY, or larger (a level picks the largest that stays small in
+                   // shared memory: a tile is a short chain of dependent memory round trips, bigger tiles amortise it)
 #define FB_MAX_FUSED_LEVELS 8
 struct BrLevel {
     const float* gk;
@@ -237,6 +240,7 @@ struct BrLevel {
     const float* ty;
     float* img;
     int w, h, ksz, fr_max, fc_pitch, tiles_x, tile_end;  // tile_end: running total of tiles up to this level
+    int tw, th;                                          // tile size in level pixels (tw a power of two <= BR_NT)
 };
 struct BrArgs {
     BrLevel lv[FB_MAX_FUSED_LEVELS];
@@ -244,7 +248,7 @@ struct BrArgs {
 };
 // All pyramid levels that need a blur go in ONE launch (coarsest = widest Gaussian first): every tile is a short
 // chain of dependent memory round trips, and the levels' chains overlap instead of running back to back.
-__global__ void __launch_bounds__(BR_TX* BR_TY) k_fb_blur_resize(const uint8_t* __restrict__ gray, int H, int W,
+__global__ void __launch_bounds__(BR_NT) k_fb_blur_resize(const uint8_t* __restrict__ gray, int H, int W,
                                                                   const __grid_constant__ BrArgs args) {
     extern __shared__ __align__(16) unsigned char br_smem[];
     int li = 0;
@@ -258,23 +262,24 @@ __global__ void __launch_bounds__(BR_TX* BR_TY) k_fb_blur_resize(const uint8_t* 
     const float* __restrict__ ty = A.ty;
     float* __restrict__ img = A.img;
     const int w = A.w, h = A.h, ksz = A.ksz, fr_max = A.fr_max, fc_pitch = A.fc_pitch;
-    float* sT = reinterpret_cast<float*>(br_smem);                   // [fr_max][BR_TX]
-    float* sG = sT + fr_max * BR_TX;                                 // [ksz]
+    const int tw = A.tw, th = A.th;
+    float* sT = reinterpret_cast<float*>(br_smem);                   // [fr_max][tw]
+    float* sG = sT + fr_max * tw;                                    // [ksz]
     unsigned char* sS = reinterpret_cast<unsigned char*>(sG + ksz);  // [fr_max][fc_pitch]
     const int tid = threadIdx.x;
-    const int x0 = (tile % A.tiles_x) * BR_TX, y0 = (tile / A.tiles_x) * BR_TY;
-    const int xl = min(x0 + BR_TX - 1, w - 1), yl = min(y0 + BR_TY - 1, h - 1);
+    const int x0 = (tile % A.tiles_x) * tw, y0 = (tile / A.tiles_x) * th;
+    const int xl = min(x0 + tw - 1, w - 1), yl = min(y0 + th - 1, h - 1);
     const int rad = ksz >> 1;
     const int c0 = sx[x0] - rad, r0 = sy[y0] - rad;
     const int ncols = sx[xl] + 1 + rad - c0 + 1, nrows = sy[yl] + 1 + rad - r0 + 1;
-    for (int i = tid; i < ksz; i += BR_TX * BR_TY) sG[i] = gk[i];
+    for (int i = tid; i < ksz; i += BR_NT) sG[i] = gk[i];
     int off = 0;  // column of the footprint's first pixel inside its staged row
     if (c0 >= 0 && ((c0 & ~3) + ((((c0 & 3) + ncols + 3) >> 2) << 2)) <= W && (W & 3) == 0 &&
         (reinterpret_cast<uintptr_t>(gray) & 3) == 0) {
         // tiles inside the frame: aligned 32-bit loads, four independent requests per thread in flight
         off = c0 & 3;
         const int nw = (off + ncols + 3) >> 2, total = nrows * nw;
-        constexpr int NTH = BR_TX * BR_TY;
+        constexpr int NTH = BR_NT;
         for (int base = tid; base < total; base += 4 * NTH) {
             uint32_t v[4];
             int fr[4], q[4];
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(BR_TX* BR_TY) k_fb_blur_resize(const uint8_t* 
     } else {
         // tiles touching a border: one warp per footprint row, byte loads with reflected columns
         const int lane = tid & 31;
-        for (int fr = tid >> 5; fr < nrows; fr += (BR_TX * BR_TY) / 32) {
+        for (int fr = tid >> 5; fr < nrows; fr += BR_NT / 32) {
             const uint8_t* src = gray + (size_t)reflect101(r0 + fr, H) * W;
             unsigned char* dst = sS + fr * fc_pitch;
             for (int fc = lane; fc < ncols; fc += 32) dst[fc] = __ldg(src + reflect101(c0 + fc, W));
@@ -302,11 +307,11 @@ __global__ void __launch_bounds__(BR_TX* BR_TY) k_fb_blur_resize(const uint8_t* 
     __syncthreads();
     // horizontal Gaussian at the two source columns of every output column + horizontal lerp
     {
-        const int ox = tid & (BR_TX - 1);
+        const int ox = tid & (tw - 1);
         const int x = min(x0 + ox, w - 1);
         const int lc = sx[x] - sx[x0];
         const float t = tx[x];
-        for (int fr = tid / BR_TX; fr < nrows; fr += BR_TY) {
+        for (int fr = tid / tw; fr < nrows; fr += BR_NT / tw) {
             const unsigned char* row = sS + fr * fc_pitch + off + lc;
             float a = 0.f, b = 0.f;
             float v = (float)row[0];
@@ -317,28 +322,31 @@ __global__ void __launch_bounds__(BR_TX* BR_TY) k_fb_blur_resize(const uint8_t* 
                 b = fmaf(g, nv, b);
                 v = nv;
             }
-            sT[fr * BR_TX + ox] = a * (1.f - t) + b * t;
+            sT[fr * tw + ox] = a * (1.f - t) + b * t;
         }
     }
     __syncthreads();
     // vertical Gaussian at the two source rows + vertical lerp
     {
-        const int ox = tid & (BR_TX - 1), oy = tid / BR_TX;
-        const int x = x0 + ox, y = y0 + oy;
-        if (x < w && y < h) {
-            const int lr = sy[y] - sy[y0];
-            const float t = ty[y];
-            const float* col = sT + lr * BR_TX + ox;
-            float a = 0.f, b = 0.f;
-            float v = col[0];
-            for (int j = 0; j < ksz; j++) {
-                float g = sG[j];
-                float nv = col[(j + 1) * BR_TX];
-                a = fmaf(g, v, a);
-                b = fmaf(g, nv, b);
-                v = nv;
+        const int ox = tid & (tw - 1);
+        const int x = x0 + ox;
+        for (int oy = tid / tw; oy < th; oy += BR_NT / tw) {
+            const int y = y0 + oy;
+            if (x < w && y < h) {
+                const int lr = sy[y] - sy[y0];
+                const float t = ty[y];
+                const float* col = sT + lr * tw + ox;
+                float a = 0.f, b = 0.f;
+                float v = col[0];
+                for (int j = 0; j < ksz; j++) {
+                    float g = sG[j];
+                    float nv = col[(j + 1) * tw];
+                    a = fmaf(g, v, a);
+                    b = fmaf(g, nv, b);
+                    v = nv;
+                }
+                img[(size_t)y * w + x] = a * (1.f - t) + b * t;
             }
-            img[(size_t)y * w + x] = a * (1.f - t) + b * t;
         }
     }
 }
@@ -868,19 +876,32 @@ extern "C" int tf_farneback_create(tf_farneback** out, int height, int width, do
         std::vector<int> s;
         std::vector<float> t;
         if (int e = upload(&L.gk, gaussian_kernel(L.ksz, L.sigma))) return bail(e);
-        linear_table(L.w, width, s, t);
-        int fc = 0, fr = 0;
-        for (int a0 = 0; a0 < L.w; a0 += BR_TX)
-            fc = std::max(fc, s[std::min(a0 + BR_TX - 1, L.w - 1)] - s[a0] + 2 * (L.ksz / 2) + 2);
+        // tile of the fused blur+resize kernel: the largest of 64x16, 64x8, 32x8 level pixels whose footprint
+        // (gray bytes + horizontal-pass floats) stays under 17 KB of shared memory; 32x8 otherwise
+        std::vector<int> sxv, syv;
+        std::vector<float> txv, tyv;
+        linear_table(L.w, width, sxv, txv);
+        linear_table(L.h, height, syv, tyv);
+        const int cand[3][2] = {{64, 16}, {64, 8}, {BR_TX, BR_TY}};
+        for (int ci = 0; ci < 3; ci++) {
+            const int tw = cand[ci][0], th = cand[ci][1];
+            int fc = 0, fr = 0;
+            for (int a0 = 0; a0 < L.w; a0 += tw)
+                fc = std::max(fc, sxv[std::min(a0 + tw - 1, L.w - 1)] - sxv[a0] + 2 * (L.ksz / 2) + 2);
+            for (int a0 = 0; a0 < L.h; a0 += th)
+                fr = std::max(fr, syv[std::min(a0 + th - 1, L.h - 1)] - syv[a0] + 2 * (L.ksz / 2) + 2);
+            L.br_tw = tw;
+            L.br_th = th;
+            L.br_rows = fr;
+            L.br_pitch = ((fc + 3) & ~3) + 4;  // + room for the alignment offset of the 32-bit loads
+            L.br_smem = (size_t)fr * tw * 4 + (size_t)L.ksz * 4 + (size_t)fr * L.br_pitch;
+            if (L.br_smem <= 17 * 1024) break;
+        }
+        if (L.br_smem > 96 * 1024) L.br_rows = 0;  // absurdly wide Gaussians: keep the two-pass kernels
+        s = sxv; t = txv;
         if (int e = upload(&L.sx, s)) return bail(e);
         if (int e = upload(&L.tx, t)) return bail(e);
-        linear_table(L.h, height, s, t);
-        for (int a0 = 0; a0 < L.h; a0 += BR_TY)
-            fr = std::max(fr, s[std::min(a0 + BR_TY - 1, L.h - 1)] - s[a0] + 2 * (L.ksz / 2) + 2);
-        L.br_rows = fr;
-        L.br_pitch = ((fc + 3) & ~3) + 4;  // + room for the alignment offset of the 32-bit loads
-        L.br_smem = (size_t)fr * BR_TX * 4 + (size_t)L.ksz * 4 + (size_t)fr * L.br_pitch;
-        if (L.br_smem > 96 * 1024) L.br_rows = 0;  // absurdly wide Gaussians: keep the two-pass kernels
+        s = syv; t = tyv;
         if (int e = upload(&L.sy, s)) return bail(e);
         if (int e = upload(&L.ty, t)) return bail(e);
         size_t n = (size_t)L.w * L.h;
@@ -964,8 +985,9 @@ static int blur_levels(tf_farneback* h, const uint8_t* gray, cudaStream_t st) {
         BrLevel& B = args.lv[args.n++];
         B.gk = L.gk; B.sx = L.sx; B.tx = L.tx; B.sy = L.sy; B.ty = L.ty; B.img = L.img;
         B.w = L.w; B.h = L.h; B.ksz = L.ksz; B.fr_max = L.br_rows; B.fc_pitch = L.br_pitch;
-        B.tiles_x = ceil_div(L.w, BR_TX);
-        tiles += B.tiles_x * ceil_div(L.h, BR_TY);
+        B.tw = L.br_tw; B.th = L.br_th;
+        B.tiles_x = ceil_div(L.w, L.br_tw);
+        tiles += B.tiles_x * ceil_div(L.h, L.br_th);
         B.tile_end = tiles;
         smem = std::max(smem, L.br_smem);
     }
@@ -975,7 +997,7 @@ static int blur_levels(tf_farneback* h, const uint8_t* gray, cudaStream_t st) {
         TF_CUDA(cudaFuncSetAttribute(k_fb_blur_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set = true;
     }
-    k_fb_blur_resize<<<tiles, BR_TX * BR_TY, smem, st>>>(gray, h->H, h->W, args);
+    k_fb_blur_resize<<<tiles, BR_NT, smem, st>>>(gray, h->H, h->W, args);
     TF_LAUNCHED();
     return TF_OK;
 }
@@ -1092,9 +1114,10 @@ static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int var
         } else if (variant == 3) {
             if (int e = fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st))
                 return e;
-        } else if (variant == 9) {
+        } else if (variant == 9 || variant == 10) {
             const bool big = (size_t)L.w * L.h >= (size_t)400000;
-            int e = big ? fb_iterate_stage<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st)
+            int e = big ? fb_iterate_stage<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st,
+                                               variant == 10)
                         : fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st);
             if (e) return e;
         } else if (variant == 8) {
@@ -1123,7 +1146,7 @@ extern "C" int tf_farneback_solve(tf_farneback* h, int slot_left, int slot_right
     TF_REQUIRE(h && flow, TF_ERR_INVALID_ARG, "tf_farneback_solve: null argument");
     TF_REQUIRE(slot_ok(slot_left) && slot_ok(slot_right) && h->has_frame[slot_left] && h->has_frame[slot_right],
                TF_ERR_INVALID_ARG, "tf_farneback_solve: slots must be prepared slots in [0, %d)", FB_SLOTS);
-    TF_REQUIRE(variant >= 0 && variant <= 9, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
+    TF_REQUIRE(variant >= 0 && variant <= 10, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
     TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_solve: flow must be 8-byte aligned");
     cudaStream_t st = as_stream(stream);
     float2* out = reinterpret_cast<float2*>(flow);
@@ -1139,7 +1162,7 @@ extern "C" int tf_farneback_step_lane(tf_farneback* h, int lane, int new_slot, c
                "tf_farneback_step: slots must be in [0, %d)", FB_SLOTS);
     TF_REQUIRE((new_slot == slot_left) != (new_slot == slot_right), TF_ERR_INVALID_ARG,
                "tf_farneback_step: the new frame must be exactly one side of the pair");
-    TF_REQUIRE(variant >= 0 && variant <= 9, TF_ERR_INVALID_ARG, "tf_farneback_step: unknown variant %d", variant);
+    TF_REQUIRE(variant >= 0 && variant <= 10, TF_ERR_INVALID_ARG, "tf_farneback_step: unknown variant %d", variant);
     TF_REQUIRE(variant != 1 || lane == 0, TF_ERR_INVALID_ARG,
                "tf_farneback_step: the unfused reference kernels (variant 1) share their scratch, lane 0 only");
     TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_step: flow must be 8-byte aligned");

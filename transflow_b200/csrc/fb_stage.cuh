@@ -67,12 +67,14 @@ struct FbsGeom {
     static constexpr size_t QBYTES = (size_t)BH * BW * 16;
     static constexpr size_t EBYTES = (size_t)BH * EP * 4;
     static constexpr size_t SMEM = RING + QBYTES + EBYTES + 32;  // + mbarrier, box origin
+    static constexpr int FIT = (int)((227 * 1024) / (SMEM + 1024));
+    static constexpr int CTAS = FIT < 1 ? 1 : (FIT > 4 ? 4 : FIT);  // resident CTAs the launch bounds ask for
 };
 
 // NT compute threads + one producer warp (threads NT .. NT + 31) that only issues the bulk copies: the per-row
 // copies are serialised by the uniform datapath, a compute warp doing it would hold up its CTA at the next barrier.
 template <int MR, int TX, int NT, int GM>
-__global__ void __launch_bounds__(NT + 32, 2)
+__global__ void __launch_bounds__(NT + 32, (FbsGeom<MR, TX, GM>::CTAS))
     k_fb_iter_stage(const float4* __restrict__ R0q, const float* __restrict__ R0e, const float4* __restrict__ R1q,
                     const float* __restrict__ R1e, const float2* __restrict__ flow_in, float2* __restrict__ flow_out,
                     int w, int h, float reg, int rows_per_cta, int clip) {
@@ -248,7 +250,8 @@ static int fb_launch_stage(const float* R0, const float* R1, const float2* in, f
 // the half-buffer kernel
 template <typename RT>
 static int fb_iterate_stage(tf_farneback* h, FbLevel& L, const RT* R0, const RT* R1, float2* final_buf,
-                            float2* other_buf, bool zero_init, int clip, bool finest, cudaStream_t st) {
+                            float2* other_buf, bool zero_init, int clip, bool finest, cudaStream_t st,
+                            bool narrow = false) {
     int m = h->winsize / 2;
     if (m != 7 || sizeof(RT) != 4 || (L.w & 3) != 0)
         return fb_iterate_half<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip, finest, 6, st);
@@ -264,7 +267,9 @@ static int fb_iterate_stage(tf_farneback* h, FbLevel& L, const RT* R0, const RT*
         int e;
         {
             ScopedKernelTimer timer(finest ? TFK_FB_ITER_FINEST : -1, st);
-            e = fb_launch_stage<7, 64, 256, 3>(R0f, R1f, in, dst, L.w, L.h, scale, c, st);
+            // narrow (variant 10): 32-column strips, 192 + 32 threads: ring 29 KB + box 23 KB -> 4 CTAs per SM
+            e = narrow ? fb_launch_stage<7, 32, 192, 3>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)
+                       : fb_launch_stage<7, 64, 256, 3>(R0f, R1f, in, dst, L.w, L.h, scale, c, st);
         }
         if (e) return e;
         TF_LAUNCHED();
