@@ -57,7 +57,7 @@ __device__ __forceinline__ void fbs_bulk_g2s(uint32_t dst, const void* src, uint
 }
 __device__ __forceinline__ void fbs_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int MR, int TX, int GM>
+template <int MR, int TX, int GM, bool S0 = false>
 struct FbsGeom {
     using G = FbhGeom<MR, TX, true>;
     static constexpr int BH = G::TY + 2 * GM + 1;            // box rows
@@ -66,27 +66,42 @@ struct FbsGeom {
     static constexpr size_t RING = G::SMEM;
     static constexpr size_t QBYTES = (size_t)BH * BW * 16;
     static constexpr size_t EBYTES = (size_t)BH * EP * 4;
-    static constexpr size_t SMEM = RING + QBYTES + EBYTES + 32;  // + mbarrier, box origin
+    // S0: the half's own R0 quads / fifth plane / flow (TY rows x COLS columns) are staged too
+    static constexpr int E0P = ((G::COLS + 3) & ~3) + 4;     // R0 fifth-plane row pitch (floats), 4-aligned start
+    static constexpr int F0P = ((G::COLS + 1) & ~1) + 2;     // flow row pitch (float2), 2-aligned start
+    static constexpr size_t Q0BYTES = S0 ? (size_t)G::TY * G::COLS * 16 : 0;
+    static constexpr size_t E0BYTES = S0 ? (size_t)G::TY * E0P * 4 : 0;
+    static constexpr size_t F0BYTES = S0 ? (size_t)G::TY * F0P * 8 : 0;
+    static constexpr size_t SMEM = RING + QBYTES + EBYTES + Q0BYTES + E0BYTES + F0BYTES + 32;  // + mbarrier, box origin
     static constexpr int FIT = (int)((227 * 1024) / (SMEM + 1024));
     static constexpr int CTAS = FIT < 1 ? 1 : (FIT > 4 ? 4 : FIT);  // resident CTAs the launch bounds ask for
 };
 
 // NT compute threads + one producer warp (threads NT .. NT + 31) that only issues the bulk copies: the per-row
 // copies are serialised by the uniform datapath, a compute warp doing it would hold up its CTA at the next barrier.
-template <int MR, int TX, int NT, int GM>
-__global__ void __launch_bounds__(NT + 32, (FbsGeom<MR, TX, GM>::CTAS))
+template <int MR, int TX, int NT, int GM, bool S0>
+__global__ void __launch_bounds__(NT + 32, (FbsGeom<MR, TX, GM, S0>::CTAS))
     k_fb_iter_stage(const float4* __restrict__ R0q, const float* __restrict__ R0e, const float4* __restrict__ R1q,
                     const float* __restrict__ R1e, const float2* __restrict__ flow_in, float2* __restrict__ flow_out,
                     int w, int h, float reg, int rows_per_cta, int clip) {
     using G = FbhGeom<MR, TX, true>;
-    using B = FbsGeom<MR, TX, GM>;
+    using B = FbsGeom<MR, TX, GM, S0>;
     constexpr int NG = NT / G::COLS;
     static_assert(NT >= G::COLS && B::BH <= 32, "one lane per box row");
-    extern __shared__ __align__(16) float ring[];  // [5][2 halves][TY][PITCH] | box quads | box fifth plane | mbarrier
+    // [5][2 halves][TY][PITCH] | box quads | box fifth plane | R0 quads | R0 fifth plane | flow | mbarrier
+    extern __shared__ __align__(16) float ring[];
     float4* boxq = reinterpret_cast<float4*>(reinterpret_cast<char*>(ring) + B::RING);
     float* boxe = reinterpret_cast<float*>(reinterpret_cast<char*>(boxq) + B::QBYTES);
+    float4* t0q = reinterpret_cast<float4*>(reinterpret_cast<char*>(boxe) + B::EBYTES);
+    float* t0e = reinterpret_cast<float*>(reinterpret_cast<char*>(t0q) + B::Q0BYTES);
+    float2* t0f = reinterpret_cast<float2*>(reinterpret_cast<char*>(t0e) + B::E0BYTES);
     // ctl: [0..1] "full" mbarrier, [2..3] "empty" mbarrier, [4] bx0, [5] by0, [6] ex0
-    int* ctl = reinterpret_cast<int*>(reinterpret_cast<char*>(boxe) + B::EBYTES);
+    int* ctl = reinterpret_cast<int*>(reinterpret_cast<char*>(t0f) + B::F0BYTES);
+    // S0: columns of the half's own operands that exist in the image (quads exactly, the other two widened to
+    // 16-byte boundaries: w % 4 == 0)
+    const int tq0 = max((int)blockIdx.x * TX - MR, 0), tq1 = min((int)blockIdx.x * TX + TX + MR, w);
+    const int te0 = tq0 & ~3, te1 = min((tq1 + 3) & ~3, w);
+    const int tf0 = tq0 & ~1, tf1 = min((tq1 + 1) & ~1, w);
     const uint32_t bar = fbh_smem_u32(ctl), bar_empty = fbh_smem_u32(ctl + 2);
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TX;
@@ -119,10 +134,11 @@ __global__ void __launch_bounds__(NT + 32, (FbsGeom<MR, TX, GM>::CTAS))
         const int ex0 = ce0;                                                    // column of boxe[row][0]
         const int ra = max(by0, 0), rb = min(by0 + B::BH, h);                   // rows [ra, rb)
         const bool any = cq1 > cq0 && rb > ra;
+        const uint32_t row0_bytes = S0 ? (uint32_t)((tq1 - tq0) * 16 + (te1 - te0) * 4 + (flow_in ? (tf1 - tf0) * 8 : 0)) : 0u;
         if (lane == 0) {
             ctl[4] = bx0; ctl[5] = by0; ctl[6] = ex0;
             const uint32_t per_row = any ? (uint32_t)((cq1 - cq0) * 16 + (ce1 - ce0) * 4) : 0u;
-            fbs_mbar_expect_tx(bar, per_row * (uint32_t)max(rb - ra, 0));
+            fbs_mbar_expect_tx(bar, per_row * (uint32_t)max(rb - ra, 0) + row0_bytes * (uint32_t)G::TY);
         }
         fbs_fence_proxy_async();  // the box was read through the generic proxy until the barrier before this call
         __syncwarp();
@@ -132,6 +148,15 @@ __global__ void __launch_bounds__(NT + 32, (FbsGeom<MR, TX, GM>::CTAS))
                          (uint32_t)(cq1 - cq0) * 16u, bar);
             fbs_bulk_g2s(fbh_smem_u32(boxe + lane * B::EP), R1e + (unsigned)row * uw + (unsigned)ce0,
                          (uint32_t)(ce1 - ce0) * 4u, bar);
+        }
+        if (S0 && lane < G::TY) {  // the half's own rows (clamped to the image like phase A clamps them)
+            const unsigned grow = (unsigned)clampi(gy_base + lane, 0, h - 1) * uw;
+            fbs_bulk_g2s(fbh_smem_u32(t0q + lane * G::COLS + (tq0 - (x0 - MR))), R0q + grow + (unsigned)tq0,
+                         (uint32_t)(tq1 - tq0) * 16u, bar);
+            fbs_bulk_g2s(fbh_smem_u32(t0e + lane * B::E0P), R0e + grow + (unsigned)te0, (uint32_t)(te1 - te0) * 4u, bar);
+            if (flow_in)
+                fbs_bulk_g2s(fbh_smem_u32(t0f + lane * B::F0P), flow_in + grow + (unsigned)tf0,
+                             (uint32_t)(tf1 - tf0) * 8u, bar);
         }
     };
 
@@ -159,10 +184,16 @@ __global__ void __launch_bounds__(NT + 32, (FbsGeom<MR, TX, GM>::CTAS))
             auto fetch = [&](int rr, int& gyo, float2& fo, float4& qo, float& eo) {
                 if (rr < G::TY) {
                     gyo = clampi(gy_base + rr, 0, h - 1);
-                    const unsigned at = (unsigned)gyo * uw + (unsigned)gxA;
-                    fo = flow_in ? __ldg(flow_in + at) : make_float2(0.f, 0.f);
-                    qo = __ldg(R0q + at);
-                    eo = __ldg(R0e + at);
+                    if (S0) {  // staged: row rr of the half, column gxA
+                        fo = flow_in ? t0f[rr * B::F0P + (gxA - tf0)] : make_float2(0.f, 0.f);
+                        qo = t0q[rr * G::COLS + (gxA - (x0 - MR))];
+                        eo = t0e[rr * B::E0P + (gxA - te0)];
+                    } else {
+                        const unsigned at = (unsigned)gyo * uw + (unsigned)gxA;
+                        fo = flow_in ? __ldg(flow_in + at) : make_float2(0.f, 0.f);
+                        qo = __ldg(R0q + at);
+                        eo = __ldg(R0e + at);
+                    }
                 }
             };
             int r = rA;
@@ -215,12 +246,12 @@ __global__ void __launch_bounds__(NT + 32, (FbsGeom<MR, TX, GM>::CTAS))
     }
 }
 
-template <int MR, int TX, int NT, int GM>
+template <int MR, int TX, int NT, int GM, bool S0 = false>
 static int fb_launch_stage(const float* R0, const float* R1, const float2* in, float2* dst, int w, int h, double scale,
                            int clip, cudaStream_t st) {
     using G = FbhGeom<MR, TX, true>;
-    using B = FbsGeom<MR, TX, GM>;
-    auto kern = k_fb_iter_stage<MR, TX, NT, GM>;
+    using B = FbsGeom<MR, TX, GM, S0>;
+    auto kern = k_fb_iter_stage<MR, TX, NT, GM, S0>;
     static int resident = 0;
     if (!resident) {
         TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::SMEM));
@@ -251,7 +282,7 @@ static int fb_launch_stage(const float* R0, const float* R1, const float2* in, f
 template <typename RT>
 static int fb_iterate_stage(tf_farneback* h, FbLevel& L, const RT* R0, const RT* R1, float2* final_buf,
                             float2* other_buf, bool zero_init, int clip, bool finest, cudaStream_t st,
-                            bool narrow = false) {
+                            int kind = 0) {
     int m = h->winsize / 2;
     if (m != 7 || sizeof(RT) != 4 || (L.w & 3) != 0)
         return fb_iterate_half<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip, finest, 6, st);
@@ -267,9 +298,11 @@ static int fb_iterate_stage(tf_farneback* h, FbLevel& L, const RT* R0, const RT*
         int e;
         {
             ScopedKernelTimer timer(finest ? TFK_FB_ITER_FINEST : -1, st);
-            // narrow (variant 10): 32-column strips, 192 + 32 threads: ring 29 KB + box 23 KB -> 4 CTAs per SM
-            e = narrow ? fb_launch_stage<7, 32, 192, 3>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)
-                       : fb_launch_stage<7, 64, 256, 3>(R0f, R1f, in, dst, L.w, L.h, scale, c, st);
+            // kind 1 (variant 10): 32-column strips, 192 + 32 threads: ring 29 KB + box 23 KB -> 4 CTAs per SM
+            // kind 2 (variant 11): as 1, with the half's own R0 / flow rows staged as well -> 3 CTAs per SM
+            e = kind == 2   ? fb_launch_stage<7, 32, 192, 3, true>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)
+                : kind == 1 ? fb_launch_stage<7, 32, 192, 3>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)
+                            : fb_launch_stage<7, 64, 256, 3>(R0f, R1f, in, dst, L.w, L.h, scale, c, st);
         }
         if (e) return e;
         TF_LAUNCHED();
