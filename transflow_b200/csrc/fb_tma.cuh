@@ -109,16 +109,19 @@ __global__ void __launch_bounds__(NT + 32, (FbmGeom<MR, TX, GM>::CTAS))
     __syncthreads();
     if (tid >= NT) {  // producer warp: one lane issues the five tensor copies of half hh once the buffer is free
         if (tid == NT) {
+            // the flow at the centre of a half (origin of its R1 box) is requested one half ahead, so that the load is
+            // not on the path between "buffer free" and the tensor copies
+            auto centre = [&](int hh) {
+                const int cy = clampi(y0 - MR + hh * G::TY + G::TY / 2, 0, h - 1), cx = clampi(x0 + TX / 2, 0, w - 1);
+                return flow_in ? __ldg(flow_in + (unsigned)cy * uw + (unsigned)cx) : make_float2(0.f, 0.f);
+            };
+            float2 fc = centre(0);
             for (int hh = 0; hh <= ntiles; hh++) {
                 if (hh > 0 && !fbm_mbar_wait(bar_empty, (uint32_t)((hh - 1) & 1))) return;
                 const int gy_base = y0 - MR + hh * G::TY;
-                int ox = 0, oy = 0;
-                if (flow_in) {
-                    const int cy = clampi(gy_base + G::TY / 2, 0, h - 1), cx = clampi(x0 + TX / 2, 0, w - 1);
-                    const float2 f = __ldg(flow_in + (unsigned)cy * uw + (unsigned)cx);
-                    ox = __float2int_rd(fminf(fmaxf(f.x, -4096.f), 4096.f));
-                    oy = __float2int_rd(fminf(fmaxf(f.y, -4096.f), 4096.f));
-                }
+                const int ox = __float2int_rd(fminf(fmaxf(fc.x, -4096.f), 4096.f));
+                const int oy = __float2int_rd(fminf(fmaxf(fc.y, -4096.f), 4096.f));
+                if (hh < ntiles) fc = centre(hh + 1);
                 const int bx0 = x0 - MR - GM + ox, by0 = gy_base - GM + oy;
                 const int ty0 = min(gy_base, h - 1);  // keeps row h - 1 inside the tile of a half below the image
                 ctl[4] = bx0; ctl[5] = by0; ctl[6] = ty0;
@@ -248,10 +251,11 @@ static int fb_launch_tma(const float* R0, const float* R1, const float2* in, flo
     return TF_OK;
 }
 
-// variant 12: 32-column strips (a 64-column box of quads would exceed the 256-element box limit of a tensor map)
+// variants 12 / 13 / 14: 32-column strips (a 64-column box of quads would exceed the 256-element box limit of a 2-D
+// tensor map), box margin 3 / 2 / 1 pixels around the footprint displaced by the centre flow
 template <typename RT>
 static int fb_iterate_tma(tf_farneback* h, FbLevel& L, const RT* R0, const RT* R1, float2* final_buf, float2* other_buf,
-                          bool zero_init, int clip, bool finest, cudaStream_t st) {
+                          bool zero_init, int clip, bool finest, cudaStream_t st, int margin = 3) {
     int m = h->winsize / 2;
     if (m != 7 || sizeof(RT) != 4 || (L.w & 3) != 0)
         return fb_iterate_half<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip, finest, 6, st);
@@ -267,7 +271,9 @@ static int fb_iterate_tma(tf_farneback* h, FbLevel& L, const RT* R0, const RT* R
         int e;
         {
             ScopedKernelTimer timer(finest ? TFK_FB_ITER_FINEST : -1, st);
-            e = fb_launch_tma<7, 32, 192, 3>(R0f, R1f, in, dst, L.w, L.h, scale, c, st);
+            e = margin == 1   ? fb_launch_tma<7, 32, 192, 1>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)
+                : margin == 2 ? fb_launch_tma<7, 32, 192, 2>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)
+                              : fb_launch_tma<7, 32, 192, 3>(R0f, R1f, in, dst, L.w, L.h, scale, c, st);
         }
         if (e) return e;
         TF_LAUNCHED();
