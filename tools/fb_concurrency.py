@@ -88,7 +88,9 @@ def main():
             print(f"{W}x{H} handles {n}: {pps:8.1f} pairs/s aggregate, {ms:.3f} ms per round", flush=True)
         return
     from transflow_b200 import _lib
-    for rows in (0, 84, 112, 168, 224, 280, 0):
+    import os
+    for rows in ([int(v) for v in os.environ["CONC_ROWS"].split(",")] if "CONC_ROWS" in os.environ
+                 else (0, 84, 112, 168, 224, 280, 0)):
         _lib.check(_lib.load().tf_farneback_tune(0, rows))
         line = f"{W}x{H} rows/CTA {rows:3d}:"
         for lanes in (1, 2):
