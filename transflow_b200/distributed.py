@@ -238,24 +238,34 @@ def bench_sharded(args, rank, world, local):
     grays = [torch.empty((H, W), dtype=torch.uint8, device="cuda") for _ in range(lanes)]
     lane_streams = [torch.cuda.Stream() for _ in range(lanes)] if lanes > 1 else None
 
+    chunk_state = {"next": None, "n": 0}
+
     def estimate_chunk(first_pair, n_pairs, outs=None):
-        """K consecutive pairs: K + 1 prepares (one extra per chunk), K solves + post-processes.
-        ``outs`` (raw device addresses, possibly peer memory) receive the post-processed flows."""
+        """K consecutive pairs: K solves + post-processes, and one extra prepare when the chunk does not continue
+        the previous one (a rank's chunks of a round are consecutive in frame order: the lanes then run on without
+        a new prepare and without draining).  ``outs`` (raw device addresses, possibly peer memory) receive the
+        post-processed flows."""
         main = torch.cuda.current_stream()
-        ops.gray_from_bgr(frame(first_pair), grays[0])
-        fb.prepare(0, grays[0])
-        if lane_streams:
-            for s in lane_streams:
-                s.wait_stream(main)
+        cont = lane_streams is not None and chunk_state["next"] == first_pair
+        if not cont:
+            ops.gray_from_bgr(frame(first_pair), grays[0])
+            fb.prepare(0, grays[0])
+            chunk_state["n"] = 0
+            if lane_streams:        # also orders the lanes after the ring's "slot free" wait of a new round
+                for s in lane_streams:
+                    s.wait_stream(main)
         flows = []
         for i in range(n_pairs):
-            lane = i % lanes
+            n = chunk_state["n"]
+            lane = n % lanes
             with torch.cuda.stream(lane_streams[lane] if lane_streams else main):
-                old, new = i % nslots, (i + 1) % nslots
+                old, new = n % nslots, (n + 1) % nslots
                 ops.gray_from_bgr(frame(first_pair + i + 1), grays[lane])
                 flow = fb.step(new, grays[lane], old, new, lane=lane)   # prepare(new) overlapped with solve: forward
                 flow.record_stream(main)
                 flows.append(posts[lane](flow, None if outs is None else outs[i]))
+            chunk_state["n"] = n + 1
+        chunk_state["next"] = first_pair + n_pairs
         if lane_streams:
             for s in lane_streams:
                 main.wait_stream(s)
