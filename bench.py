@@ -57,11 +57,33 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.begin = 0          # first line that belongs to the timed region (mark_begin)
+        self.end = None         # one past its last line (mark_end); None = everything up to stop()
+        self.window = "timed region"
+
+    def mark_begin(self):
+        self.begin = len(self.lines)
+
+    def mark_end(self):
+        self.end = len(self.lines)
+
+    def samples_in_window(self) -> int:
+        return (len(self.lines) if self.end is None else self.end) - self.begin
+
+    def extend(self, keep_busy, want=2, limit_s=4.0):
+        """The timed region was shorter than nvidia-smi's period: keep the GPU under the SAME load (untimed steps)
+        until `want` samples have arrived, and say so in the line."""
+        t0 = time.perf_counter()
+        self.end = None
+        self.begin = len(self.lines)
+        while len(self.lines) - self.begin < want and time.perf_counter() - t0 < limit_s and self.proc is not None:
+            keep_busy()
+        self.window = "same load, right after the timed region (it was shorter than the sampling period)"
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -77,7 +99,7 @@ class ClockSampler:
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for line in self.lines[self.begin:self.end]:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
@@ -90,7 +112,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": self.window}
 
 
 def build_workload(height, width, n_frames, seed=0):
@@ -285,11 +307,12 @@ def run_ours(args):
                 for fs in flow_streams:
                     fs.wait_event(ev_free[k])
 
+    sampler = ClockSampler(local)
+    sampler.start()             # running before the warm-up, so that its first samples are not lost to start-up
     for t in range(args.warmup):
         step(t)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark_begin()
     _lib.timer_enable(True)
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -298,10 +321,23 @@ def run_ours(args):
         step(t)
     e1.record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0
     kernel_ms = {tag: _lib.timer_read(tag) for tag in _lib.KERNEL_TAGS}
     _lib.timer_enable(False)
+    if sampler.samples_in_window() < 2:
+        t_extra = [args.warmup + args.steps]
+
+        def keep_busy():
+            for _ in range(20):
+                step(t_extra[0])
+                t_extra[0] += 1
+            torch.cuda.synchronize()
+        sampler.extend(keep_busy)
+        t_after = t_extra[0]
+    else:
+        t_after = args.warmup + args.steps
     clocks = sampler.stop()
     fps = args.steps / (ms / 1000.0)
     # With two lanes a kernel's event-bracketed duration in the timed region includes the kernels of the other
@@ -312,7 +348,7 @@ def run_ours(args):
         n_serial = max(20, min(args.steps, 100))
         torch.cuda.synchronize()
         _lib.timer_enable(True)
-        t_next = args.warmup + args.steps
+        t_next = t_after
         for t in range(t_next, t_next + n_serial):
             step(t, serial=True)
         torch.cuda.synchronize()
