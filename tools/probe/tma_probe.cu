@@ -1,4 +1,5 @@
 // Probe: which 2-D tensor-copy configurations work on this box (each case in its own process).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tma_probe tma_probe.cu   (built binary is git-ignored)
 //   tma_probe <desc: 0 param, 1 global> <inner> <rows> <box_inner> <box_rows> <x> <y>
 #include <cuda.h>
 #include <cuda_runtime.h>
