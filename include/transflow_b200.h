@@ -119,7 +119,8 @@ TF_API int tf_farneback_set_debug(tf_farneback* h, int on);
 TF_API int tf_farneback_debug_read(tf_farneback* h, int slot, int level_index, int what, float* out,
                             void* stream);
 /* Tuning knob for experiments (process-wide): key 0 = rows per CTA of the variant 4-7 kernels (0 = heuristic);
- * key 1 = 1 selects the separate horizontal / vertical pyramid blur passes instead of the fused kernel. */
+ * key 1 = 1 selects the separate horizontal / vertical pyramid blur passes instead of the fused kernel;
+ * key 2 = smallest level (pixels) the key-0 override applies to. */
 TF_API int tf_farneback_tune(int key, int value);
 /* Algorithmic bytes moved per solved pair (SURVEY.md 8d model), for roofline reporting. */
 TF_API double tf_farneback_algorithmic_bytes(const tf_farneback* h, int reuse_r);

@@ -88,3 +88,44 @@ def test_video_pixmap_source_matches_reference_class(kw, tmp_path):
     assert len(got) == len(want)
     for a, b in zip(got, want):
         np.testing.assert_array_equal(a, b)
+
+
+def test_bench_clock_sampler_counts_only_the_timed_region():
+    """bench.ClockSampler: samples that arrive before mark_begin / after mark_end do not count; when the timed region
+    holds fewer than two samples the same load is kept until two have arrived and the line says so."""
+    import bench
+
+    class FakeProc:
+        def terminate(self):
+            pass
+
+    def line(mhz, power_cap="Not Active"):
+        return f"{mhz}, 1965, 700.0, Not Active, Not Active, Not Active, {power_cap}"
+
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    s.lines = [line(300), line(400)]                 # start-up, before the timed region
+    s.mark_begin()
+    s.lines += [line(1950), line(1965, "Active"), line(1965)]
+    s.mark_end()
+    s.lines += [line(210)]                           # after it
+    assert s.samples_in_window() == 3
+    out = s.stop()
+    assert out["samples"] == 3 and out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"] and out["window"] == "timed region"
+
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    s.lines = [line(300)]
+    s.mark_begin()
+    s.mark_end()                                     # a timed region shorter than the sampling period
+    assert s.samples_in_window() == 0
+    calls = []
+
+    def keep_busy():
+        calls.append(1)
+        s.lines.append(line(1900 + len(calls)))
+    s.extend(keep_busy, want=2, limit_s=5.0)
+    out = s.stop()
+    assert len(calls) == 2 and out["samples"] == 2 and out["sm_mhz"] == 1901.5
+    assert out["window"].startswith("same load")

@@ -92,6 +92,7 @@ def main():
     for rows in ([int(v) for v in os.environ["CONC_ROWS"].split(",")] if "CONC_ROWS" in os.environ
                  else (0, 84, 112, 168, 224, 280, 0)):
         _lib.check(_lib.load().tf_farneback_tune(0, rows))
+        _lib.check(_lib.load().tf_farneback_tune(2, int(os.environ.get("CONC_MIN_PX", "0"))))
         line = f"{W}x{H} rows/CTA {rows:3d}:"
         for lanes in (1, 2):
             line += f"  lanes {lanes}: {run_lanes(lanes, frames, H, W, steps):7.1f} pairs/s"

@@ -772,9 +772,11 @@ static int g_fb_two_pass = 0;  // tf_farneback_tune(1, ..): separate blur passes
 #include "fb_tma.cuh"
 
 int g_fbh_rows = 0;
+int g_fbh_rows_min_px = 0;
 extern "C" int tf_farneback_tune(int key, int value) {
     if (key == 0) g_fbh_rows = value;
     else if (key == 1) g_fb_two_pass = value;
+    else if (key == 2) g_fbh_rows_min_px = value;
     else return fail(TF_ERR_INVALID_ARG, "tf_farneback_tune: unknown key %d", key);
     return TF_OK;
 }

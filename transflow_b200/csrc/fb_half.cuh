@@ -333,6 +333,7 @@ __global__ void __launch_bounds__(NT, (FbhCfg<MR, TX, NT, WANT, VEC>::CTAS))
 
 // tuning knobs for experiments (0 = heuristic): rows per CTA, via tf_farneback_tune
 extern int g_fbh_rows;
+extern int g_fbh_rows_min_px;  // the rows override applies to levels of at least this many pixels (key 2)
 
 template <int MR, int TX, int NT, int WANT, bool VEC>
 static int fb_launch_half(const float* R0, const float* R1, const float2* in, float2* dst, int w, int h, double scale,
@@ -352,7 +353,7 @@ static int fb_launch_half(const float* R0, const float* R1, const float2* in, fl
     int strips = ceil_div(w, TX);
     int sms = sm_count();
     int rows;
-    if (g_fbh_rows > 0) {
+    if (g_fbh_rows > 0 && (size_t)w * h >= (size_t)g_fbh_rows_min_px) {
         rows = ceil_div(g_fbh_rows, G::TY) * G::TY;
     } else {
         const double wave = (double)resident * sms;
