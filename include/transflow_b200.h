@@ -77,10 +77,11 @@ TF_API int tf_farneback_destroy(tf_farneback* h);
  * on first use and only needed by tf_farneback_step_lane). */
 TF_API int tf_farneback_prepare(tf_farneback* h, int slot, const uint8_t* gray, void* stream);
 /* Coarse-to-fine displacement solve between two prepared slots -> flow (H, W, 2).
- * variant: 9-14 = experimental staged kernels, all bit-identical to 8 and slower on B200:
+ * variant: 9-16 = experimental staged kernels, all bit-identical to 8 and slower on B200:
  * 9 / 10 = R1 operand staged in shared memory by per-row bulk copies, 64- / 32-column strips (fb_stage.cuh);
  * 11 = 10 with the half's own R0 / flow rows staged too; 12 / 13 / 14 = every operand by 2-D bulk tensor copies,
- * box margin 3 / 2 / 1 px (fb_tma.cuh); 8 = default: fused half-buffer iteration kernel (fb_half.cuh) on pyramid levels of >= 0.4 Mpx, fused
+ * box margin 3 / 2 / 1 px (fb_tma.cuh), 15 / 16 = 14 with two sets of operand buffers (192 / 384 compute
+ * threads); 8 = default: fused half-buffer iteration kernel (fb_half.cuh) on pyramid levels of >= 0.4 Mpx, fused
  * rolling-tile kernel (fb_tile.cuh) on the smaller ones; 4-7 = half-buffer kernel everywhere (scalar or 128-bit
  * shared accesses, 4 or 3 CTAs per SM); 3 = rolling-tile kernel everywhere; 1 = unfused reference kernels
  * (M and double vertical sums materialised in HBM); 0 / 2 = fused column-streaming kernel with

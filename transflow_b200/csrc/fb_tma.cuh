@@ -15,7 +15,7 @@
 #include <cuda.h>
 #include "fb_stage.cuh"
 
-template <int MR, int TX, int GM>
+template <int MR, int TX, int GM, int NBUF = 1>
 struct FbmGeom {
     using G = FbhGeom<MR, TX, true>;
     static constexpr int BH = G::TY + 2 * GM + 1;           // R1 box rows
@@ -32,7 +32,8 @@ struct FbmGeom {
     static constexpr size_t Q0 = al((size_t)G::TY * TW * 16), E0 = al((size_t)G::TY * TE * 4), F0 = al((size_t)G::TY * TF * 8);
     static constexpr uint32_t TX_BYTES_NOFLOW = (uint32_t)(BH * BW * 16 + BH * BE * 4 + G::TY * TW * 16 + G::TY * TE * 4);
     static constexpr uint32_t TX_BYTES_FLOW = TX_BYTES_NOFLOW + (uint32_t)(G::TY * TF * 8);
-    static constexpr size_t SMEM = RING + Q1 + E1 + Q0 + E0 + F0 + 128;  // + mbarriers, box origin
+    static constexpr size_t OPB = Q1 + E1 + Q0 + E0 + F0;                // one set of operand buffers
+    static constexpr size_t SMEM = RING + NBUF * OPB + 128;              // + mbarriers, box origins
     static constexpr int FIT = (int)((227 * 1024) / (SMEM + 1024));
     static constexpr int CTAS = FIT < 1 ? 1 : (FIT > 4 ? 4 : FIT);
 };
@@ -71,25 +72,24 @@ __device__ __forceinline__ bool fbm_mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
-template <int MR, int TX, int NT, int GM>
-__global__ void __launch_bounds__(NT + 32, (FbmGeom<MR, TX, GM>::CTAS))
+template <int MR, int TX, int NT, int GM, int NBUF>
+__global__ void __launch_bounds__(NT + 32, (FbmGeom<MR, TX, GM, NBUF>::CTAS))
     k_fb_iter_tma(const __grid_constant__ FbmMaps maps, const float4* __restrict__ R1q, const float* __restrict__ R1e,
                   const float2* __restrict__ flow_in, float2* __restrict__ flow_out, int w, int h, float reg,
                   int rows_per_cta, int clip) {
     using G = FbhGeom<MR, TX, true>;
-    using B = FbmGeom<MR, TX, GM>;
+    using B = FbmGeom<MR, TX, GM, NBUF>;
     constexpr int NG = NT / G::COLS;
     static_assert(NT >= G::COLS, "one thread per halo'd column needed");
+    static_assert(NBUF == 1 || NBUF == 2, "one or two sets of operand buffers");
     extern __shared__ __align__(128) float ring[];
     char* base = reinterpret_cast<char*>(ring);
-    float4* boxq = reinterpret_cast<float4*>(base + B::RING);
-    float* boxe = reinterpret_cast<float*>(base + B::RING + B::Q1);
-    float4* t0q = reinterpret_cast<float4*>(base + B::RING + B::Q1 + B::E1);
-    float* t0e = reinterpret_cast<float*>(base + B::RING + B::Q1 + B::E1 + B::Q0);
-    float2* t0f = reinterpret_cast<float2*>(base + B::RING + B::Q1 + B::E1 + B::Q0 + B::E0);
-    // ctl: [0..1] "full" mbarrier, [2..3] "empty" mbarrier, [4] bx0, [5] by0, [6] ty0
-    int* ctl = reinterpret_cast<int*>(base + B::RING + B::Q1 + B::E1 + B::Q0 + B::E0 + B::F0);
-    const uint32_t bar = fbh_smem_u32(ctl), bar_empty = fbh_smem_u32(ctl + 2);
+    // operand set s (half hh uses set hh % NBUF): R1 box quads | fifth plane | own quads | own fifth plane | own flow
+    auto set_base = [&](int s) { return base + B::RING + (size_t)s * B::OPB; };
+    // ctl: "full" mbarrier of set s at [4 s], "empty" at [4 s + 2]; origins (bx0, by0, ty0) of set s at [8 + 4 s ..]
+    int* ctl = reinterpret_cast<int*>(base + B::RING + NBUF * B::OPB);
+    auto bar_full = [&](int s) { return fbh_smem_u32(ctl + 4 * s); };
+    auto bar_empty = [&](int s) { return fbh_smem_u32(ctl + 4 * s + 2); };
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TX;
     const int y0 = blockIdx.y * rows_per_cta;
@@ -103,11 +103,13 @@ __global__ void __launch_bounds__(NT + 32, (FbmGeom<MR, TX, GM>::CTAS))
     const unsigned uw = (unsigned)w;
 
     if (tid == 0) {
-        fbs_mbar_init(bar, 1);
-        fbs_mbar_init(bar_empty, 1);
+        for (int s = 0; s < NBUF; s++) {
+            fbs_mbar_init(bar_full(s), 1);
+            fbs_mbar_init(bar_empty(s), 1);
+        }
     }
     __syncthreads();
-    if (tid >= NT) {  // producer warp: one lane issues the five tensor copies of half hh once the buffer is free
+    if (tid >= NT) {  // producer warp: one lane issues the five tensor copies of half hh once its set is free
         if (tid == NT) {
             // the flow at the centre of a half (origin of its R1 box) is requested one half ahead, so that the load is
             // not on the path between "buffer free" and the tensor copies
@@ -117,14 +119,22 @@ __global__ void __launch_bounds__(NT + 32, (FbmGeom<MR, TX, GM>::CTAS))
             };
             float2 fc = centre(0);
             for (int hh = 0; hh <= ntiles; hh++) {
-                if (hh > 0 && !fbm_mbar_wait(bar_empty, (uint32_t)((hh - 1) & 1))) return;
+                const int s = hh % NBUF, use = hh / NBUF;  // the use-th fill of set s
+                if (use > 0 && !fbm_mbar_wait(bar_empty(s), (uint32_t)((use - 1) & 1))) return;
+                const uint32_t bar = bar_full(s);
+                char* ob = set_base(s);
+                float4* boxq = reinterpret_cast<float4*>(ob);
+                float* boxe = reinterpret_cast<float*>(ob + B::Q1);
+                float4* t0q = reinterpret_cast<float4*>(ob + B::Q1 + B::E1);
+                float* t0e = reinterpret_cast<float*>(ob + B::Q1 + B::E1 + B::Q0);
+                float2* t0f = reinterpret_cast<float2*>(ob + B::Q1 + B::E1 + B::Q0 + B::E0);
                 const int gy_base = y0 - MR + hh * G::TY;
                 const int ox = __float2int_rd(fminf(fmaxf(fc.x, -4096.f), 4096.f));
                 const int oy = __float2int_rd(fminf(fmaxf(fc.y, -4096.f), 4096.f));
                 if (hh < ntiles) fc = centre(hh + 1);
                 const int bx0 = x0 - MR - GM + ox, by0 = gy_base - GM + oy;
                 const int ty0 = min(gy_base, h - 1);  // keeps row h - 1 inside the tile of a half below the image
-                ctl[4] = bx0; ctl[5] = by0; ctl[6] = ty0;
+                ctl[8 + 4 * s] = bx0; ctl[9 + 4 * s] = by0; ctl[10 + 4 * s] = ty0;
                 fbs_fence_proxy_async();  // the buffers were read through the generic proxy until the last barrier
                 fbs_mbar_expect_tx(bar, flow_in ? B::TX_BYTES_FLOW : B::TX_BYTES_NOFLOW);
                 fbm_tensor_g2s(fbh_smem_u32(t0q), &maps.r0q, 4 * tx0, ty0, bar);
@@ -139,9 +149,16 @@ __global__ void __launch_bounds__(NT + 32, (FbmGeom<MR, TX, GM>::CTAS))
 
     for (int hh = 0; hh <= ntiles; hh++) {
         float* new_half = ring + (hh & 1) * G::HALF;
-        if (!fbm_mbar_wait(bar, (uint32_t)(hh & 1))) return;
+        const int s = hh % NBUF, use = hh / NBUF;
+        if (!fbm_mbar_wait(bar_full(s), (uint32_t)(use & 1))) return;
         if (activeA) {
-            const int bx0 = ctl[4], by0 = ctl[5], ty0 = ctl[6];
+            const char* ob = set_base(s);
+            const float4* boxq = reinterpret_cast<const float4*>(ob);
+            const float* boxe = reinterpret_cast<const float*>(ob + B::Q1);
+            const float4* t0q = reinterpret_cast<const float4*>(ob + B::Q1 + B::E1);
+            const float* t0e = reinterpret_cast<const float*>(ob + B::Q1 + B::E1 + B::Q0);
+            const float2* t0f = reinterpret_cast<const float2*>(ob + B::Q1 + B::E1 + B::Q0 + B::E0);
+            const int bx0 = ctl[8 + 4 * s], by0 = ctl[9 + 4 * s], ty0 = ctl[10 + 4 * s];
             const int gy_base = y0 - MR + hh * G::TY;
             const int lx0 = gxA - tx0, le0 = gxA - (tx0 & ~3), lf0 = gxA - (tx0 & ~1), ex0 = bx0 & ~3;
 #pragma unroll 1
@@ -174,8 +191,8 @@ __global__ void __launch_bounds__(NT + 32, (FbmGeom<MR, TX, GM>::CTAS))
                 for (int c = 0; c < 5; c++) dst[c * G::CHS] = mm[c];
             }
         }
-        fbs_bar_consumers<NT>();  // M of this half complete; every thread is done with the operand buffers
-        if (tid == 0) fbs_mbar_arrive(bar_empty);
+        fbs_bar_consumers<NT>();  // M of this half complete; every thread is done with this set of operands
+        if (tid == 0) fbs_mbar_arrive(bar_empty(s));
         if (hh == 0) continue;
         float* old_half = ring + ((hh & 1) ^ 1) * G::HALF;
         const int ty = y0 + (hh - 1) * G::TY;
@@ -212,12 +229,12 @@ static int fbm_map2d(CUtensorMap* m, const void* basep, uint64_t inner, uint64_t
     return TF_OK;
 }
 
-template <int MR, int TX, int NT, int GM>
+template <int MR, int TX, int NT, int GM, int NBUF = 1>
 static int fb_launch_tma(const float* R0, const float* R1, const float2* in, float2* dst, int w, int h, double scale,
                          int clip, cudaStream_t st) {
     using G = FbhGeom<MR, TX, true>;
-    using B = FbmGeom<MR, TX, GM>;
-    auto kern = k_fb_iter_tma<MR, TX, NT, GM>;
+    using B = FbmGeom<MR, TX, GM, NBUF>;
+    auto kern = k_fb_iter_tma<MR, TX, NT, GM, NBUF>;
     static int resident = 0;
     if (!resident) {
         TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::SMEM));
@@ -271,7 +288,11 @@ static int fb_iterate_tma(tf_farneback* h, FbLevel& L, const RT* R0, const RT* R
         int e;
         {
             ScopedKernelTimer timer(finest ? TFK_FB_ITER_FINEST : -1, st);
-            e = margin == 1   ? fb_launch_tma<7, 32, 192, 1>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)
+            // margin 0 / -1 (variants 15 / 16): margin 1 with TWO sets of operand buffers (the copies of half k + 1 run
+            // during the whole of half k; 2 CTAs per SM), 192 or 384 compute threads
+            e = margin == 0    ? fb_launch_tma<7, 32, 192, 1, 2>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)
+                : margin == -1 ? fb_launch_tma<7, 32, 384, 1, 2>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)
+                : margin == 1  ? fb_launch_tma<7, 32, 192, 1>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)
                 : margin == 2 ? fb_launch_tma<7, 32, 192, 2>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)
                               : fb_launch_tma<7, 32, 192, 3>(R0f, R1f, in, dst, L.w, L.h, scale, c, st);
         }
