@@ -266,7 +266,7 @@ def test_farneback_fused_pyramid_is_bit_identical_to_two_pass(shape, params):
         np.testing.assert_array_equal(fb.debug_read(0, li, 0).cpu().numpy(), ref)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 6, 8])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 6, 8, 17])
 @pytest.mark.parametrize("params", FB_PARAMS)
 @pytest.mark.parametrize("shape", [(135, 201), (480, 854)])
 def test_farneback_matches_cv2(shape, params, variant):

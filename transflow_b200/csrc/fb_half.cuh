@@ -166,10 +166,67 @@ __device__ __forceinline__ void fbh_phase_b(float* __restrict__ old_half, const 
 }
 
 // ---- phase C: horizontal window sums + 2x2 solve + store for the tile's nout rows ----
-template <typename G, int TX, int NT, bool VEC>
+template <typename G, int TX, int NT, bool VEC, int SEG = 8>
 __device__ __forceinline__ void fbh_phase_c(const float* __restrict__ old_half, float2* __restrict__ flow_out, int tid,
                                             int x0, int ty, int nout, int w, int h, float reg, int clip) {
-    {
+    if (SEG == 4) {
+        // finer split (variant 17): one thread per (row, 4-column segment), a warp = 8 segments x 4 rows, so that a
+        // 64-column strip has 8 warp items per tile instead of 4 (every warp of the CTA has work); the window is
+        // 4 + 2m floats = five 128-bit loads per channel, a quarter-warp reads 8 consecutive 16-byte groups
+        static_assert(SEG != 4 || VEC, "the 4-column split uses the vector layout");
+        constexpr int NSEG = TX / 4;
+        constexpr int WX = NSEG / 8;
+        constexpr int NQ4 = (4 + G::WIN - 1 + 3) / 4;
+        constexpr int NWI = ((G::TY + 3) / 4) * WX;
+        const int lane = tid & 31;
+        for (int wi = tid >> 5; wi < NWI; wi += NT / 32) {
+            const int seg = (lane & 7) + 8 * (wi % WX);
+            const int row = (lane >> 3) + 4 * (wi / WX);
+            if (row < nout) {
+                const int y = ty + row;
+                const int xg = x0 + seg * 4;
+                float2* dst = flow_out + (size_t)y * w + xg;
+                const bool wide = xg + 4 <= w && (w & 1) == 0;
+                const float4* rp = reinterpret_cast<const float4*>(old_half + row * G::PITCH + seg * 4);
+                float sum[5][4];
+#pragma unroll
+                for (int c = 0; c < 5; c++) {
+                    float win[4 * NQ4];
+#pragma unroll
+                    for (int k = 0; k < NQ4; k++) {
+                        float4 t = rp[c * (G::CHS / 4) + k];
+                        win[4 * k] = t.x; win[4 * k + 1] = t.y; win[4 * k + 2] = t.z; win[4 * k + 3] = t.w;
+                    }
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < G::WIN; k++) acc += win[k];
+                    sum[c][0] = acc;
+#pragma unroll
+                    for (int o = 1; o < 4; o++) {
+                        acc += win[o + G::WIN - 1] - win[o - 1];
+                        sum[c][o] = acc;
+                    }
+                }
+#pragma unroll
+                for (int o = 0; o < 4; o += 2) {
+                    float2 u = fbh_solve(sum[0][o], sum[1][o], sum[2][o], sum[3][o], sum[4][o], reg);
+                    float2 v = fbh_solve(sum[0][o + 1], sum[1][o + 1], sum[2][o + 1], sum[3][o + 1], sum[4][o + 1], reg);
+                    if (clip) {
+                        u.x = fminf(fmaxf(u.x, (float)(-(xg + o))), (float)(w - 1 - (xg + o)));
+                        u.y = fminf(fmaxf(u.y, (float)(-y)), (float)(h - 1 - y));
+                        v.x = fminf(fmaxf(v.x, (float)(-(xg + o + 1))), (float)(w - 2 - (xg + o)));
+                        v.y = fminf(fmaxf(v.y, (float)(-y)), (float)(h - 1 - y));
+                    }
+                    if (wide) {
+                        reinterpret_cast<float4*>(dst)[o >> 1] = make_float4(u.x, u.y, v.x, v.y);
+                    } else {
+                        if (xg + o < w) dst[o] = u;
+                        if (xg + o + 1 < w) dst[o + 1] = v;
+                    }
+                }
+            }
+        }
+    } else {
         constexpr int NSEG = TX / 8;
         constexpr int WX = NSEG / 4;  // warp items per group of 8 rows
         constexpr int NWI = ((G::TY + 7) / 8) * WX;
@@ -258,7 +315,7 @@ struct FbhCfg {
     static constexpr int CTAS = FIT < 1 ? 1 : (FIT > WANT ? WANT : FIT);
 };
 
-template <int MR, int TX, int NT, int WANT, bool VEC>
+template <int MR, int TX, int NT, int WANT, bool VEC, int SEG = 8>
 __global__ void __launch_bounds__(NT, (FbhCfg<MR, TX, NT, WANT, VEC>::CTAS))
     k_fb_iter_half(const float4* __restrict__ R0q, const float* __restrict__ R0e, const float4* __restrict__ R1q,
                    const float* __restrict__ R1e, const float2* __restrict__ flow_in, float2* __restrict__ flow_out,
@@ -326,7 +383,7 @@ __global__ void __launch_bounds__(NT, (FbhCfg<MR, TX, NT, WANT, VEC>::CTAS))
         __syncthreads();
         fbh_phase_b<G, NT, VEC>(old_half, new_half, tid);
         __syncthreads();
-        fbh_phase_c<G, TX, NT, VEC>(old_half, flow_out, tid, x0, ty, nout, w, h, reg, clip);
+        fbh_phase_c<G, TX, NT, VEC, SEG>(old_half, flow_out, tid, x0, ty, nout, w, h, reg, clip);
         __syncthreads();  // the next tile's phase A overwrites the half phase C just read
     }
 }
@@ -335,11 +392,11 @@ __global__ void __launch_bounds__(NT, (FbhCfg<MR, TX, NT, WANT, VEC>::CTAS))
 extern int g_fbh_rows;
 extern int g_fbh_rows_min_px;  // the rows override applies to levels of at least this many pixels (key 2)
 
-template <int MR, int TX, int NT, int WANT, bool VEC>
+template <int MR, int TX, int NT, int WANT, bool VEC, int SEG = 8>
 static int fb_launch_half(const float* R0, const float* R1, const float2* in, float2* dst, int w, int h, double scale,
                           int clip, cudaStream_t st) {
     using G = FbhGeom<MR, TX, VEC>;
-    auto kern = k_fb_iter_half<MR, TX, NT, WANT, VEC>;
+    auto kern = k_fb_iter_half<MR, TX, NT, WANT, VEC, SEG>;
     static int resident = 0;
     if (!resident) {
         TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
@@ -370,7 +427,8 @@ static int fb_launch_half(const float* R0, const float* R1, const float2* in, fl
 }
 
 // variant 4: scalar B / C, 4 CTAs / SM (64 registers); 5: 128-column strips, 512 threads, 2 CTAs / SM, vector B / C;
-// 6: vector B / C, 4 CTAs / SM (the configuration variant 8 uses); 7: scalar B / C, 3 CTAs / SM.
+// 6: vector B / C, 4 CTAs / SM; 7: scalar B / C, 3 CTAs / SM; 17: as 6 with phase C split into 4-column segments so
+// that all 8 warps of a CTA have work in it (the configuration variant 8 uses: 157 vs 169 us at 4K).
 // Window radii below 4 (tiles of fewer than 8 rows) stay on the rolling-tile kernel.
 template <typename RT>
 static int fb_iterate_half(tf_farneback* h, FbLevel& L, const RT* R0, const RT* R1, float2* final_buf,
@@ -396,6 +454,7 @@ static int fb_iterate_half(tf_farneback* h, FbLevel& L, const RT* R0, const RT* 
     case MR:                                                                                            \
         e = variant == 5   ? fb_launch_half<MR, 128, 512, 2, true>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)  \
             : variant == 6 ? fb_launch_half<MR, 64, 256, 4, true>(R0f, R1f, in, dst, L.w, L.h, scale, c, st) \
+            : variant == 17 ? fb_launch_half<MR, 64, 256, 4, true, 4>(R0f, R1f, in, dst, L.w, L.h, scale, c, st) \
             : variant == 7 ? fb_launch_half<MR, 64, 256, 3, false>(R0f, R1f, in, dst, L.w, L.h, scale, c, st) \
                            : fb_launch_half<MR, 64, 256, 4, false>(R0f, R1f, in, dst, L.w, L.h, scale, c, st); \
         break;

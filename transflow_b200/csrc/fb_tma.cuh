@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(NT + 32, (FbmGeom<MR, TX, GM, NBUF>::CTAS))
         const int nout = min(G::TY, y1 - ty);
         fbh_phase_b<G, NT, true>(old_half, new_half, tid);
         fbs_bar_consumers<NT>();
-        fbh_phase_c<G, TX, NT, true>(old_half, flow_out, tid, x0, ty, nout, w, h, reg, clip);
+        fbh_phase_c<G, TX, NT, true, 4>(old_half, flow_out, tid, x0, ty, nout, w, h, reg, clip);
         fbs_bar_consumers<NT>();  // the next half's phase A overwrites the half phase C just read
     }
 }
