@@ -368,12 +368,12 @@ def run_ours(args):
         tot_ms, n = cand[dom]
         achieved = alg[dom] / (tot_ms / n / 1000.0) / 1e9
         # DRAM traffic of the same kernel from the committed ncu --set full capture
-        # (profiles/r01_ncu_full_k_fb_iter_half.txt: 446.12 MB read + 62.08 MB written per 4K launch of the
+        # (profiles/r01_ncu_full_k_fb_iter_half_c4.txt: 453.52 MB read + 46.27 MB written per 4K launch of the
         # default kernel; the rolling-tile kernel, TFB200_FB_VARIANT=3, moved 428.36 + 58.62 MB)
         default_kernel = os.environ.get("TFB200_FB_VARIANT", "8") == "8"
         traffic = None
         if dom == "fb_iter_finest" and (H, W) == (H4K, W4K):
-            traffic = 508.20e6 if default_kernel else (486.99e6 if os.environ.get("TFB200_FB_VARIANT") == "3" else None)
+            traffic = 499.80e6 if default_kernel else (486.99e6 if os.environ.get("TFB200_FB_VARIANT") == "3" else None)
         reg_ms, reg_n = kernel_ms_region[dom]
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
