@@ -72,8 +72,12 @@ class Compositor:
 
     @classmethod
     def from_args(cls, height: int, width: int, layer_configs: list[LayerConfig],
-                  background_color: str = "#ffffff"):
+                  background_color: str = "#ffffff", seed: int | None = None):
+        """``seed`` (``Config.seed``) keys the device-side random-reset draws per layer; the reference seeds the
+        global NumPy generator instead (pipeline.py), which the ``reset_rng = "numpy"`` parity mode still follows."""
         layers = [Layer.from_args(config, height, width, []) for config in layer_configs]
+        for layer in layers:
+            layer.set_seed(seed)
         return cls(height, width, layers, background_color=background_color)
 
     def set_sources(self, pixmap_interfaces: dict[int, list[PixmapSourceInterface]]):

@@ -4,8 +4,10 @@ Public surface kept from the reference (``layer.py:11-55``, ``data.py:6-17``):
 ``Layer(config, height, width, sources)``, ``set_sources``, ``update(flow)``,
 ``render() -> uint8 (H, W, 4)``, ``from_args`` string dispatch, and the state attributes other
 code reads -- ``data`` (int32 (H, W, DEPTH)), ``rgba``, ``base``, ``INDEX_I/J/ALPHA/SOURCE``,
-``DEPTH``, ``sources``.  ``data`` / ``rgba`` are materialised from HBM on access, and
-pickling goes through the same NumPy arrays, so checkpoints interchange with the reference.
+``DEPTH``, ``sources``.  ``data`` / ``rgba`` are materialised from HBM on access, and pickling goes
+through the same NumPy arrays plus the mask arrays (the reference pickles its mask arrays too, so a
+``random`` mask survives a checkpoint).  The pickled class paths differ from the reference's, so a
+``.ckpt.zip`` is resumed by the side that wrote it.
 """
 import ctypes as C
 import os
@@ -64,6 +66,7 @@ class Layer:
         #:            draws the reference consumes (reference.py:59), for bit-exact parity.
         self.reset_rng = os.environ.get("TRANSFLOW_B200_RESET_RNG", "device")
         self.rng_seed = 0x5EED
+        self.set_seed(None)
         self._lib = _lib.load()
         self._handle = C.c_void_p()
         self._create()
@@ -94,13 +97,24 @@ class Layer:
         cfg = self._config_struct()
         check(self._lib.tf_layer_create(C.byref(self._handle), self.height, self.width, C.byref(cfg)))
 
-    def _upload_masks(self):
+    def set_seed(self, seed):
+        """Philox key of the device reset draws: one stream per (``config.seed``, layer index), so two layers with
+        ``reset_mode=random`` draw different numbers and ``Config.seed`` reproduces a run."""
+        base = 0 if seed is None else int(seed)
+        index = int(getattr(self.config, "index", 0) or 0)
+        self.rng_seed = (0x5EED + base * 0x9E3779B97F4A7C15 + index * 0xC2B2AE3D27D4EB4F) & 0xFFFFFFFFFFFFFFFF
+
+    def _upload_masks(self, arrays=None):
+        """``arrays``: the four mask arrays of a pickled layer (else they are built from the config strings)."""
         shape = (self.height, self.width)
         c = self.config
-        self.mask_alpha = load_float_mask(c.mask_alpha, shape, 1)
-        self.mask_src = load_bool_mask(c.mask_src, shape, True)
-        self.mask_dst = load_bool_mask(c.mask_dst, shape, True)
-        self.reset_mask = load_float_mask(c.reset_mask, shape, 1)
+        if arrays is not None:
+            self.mask_alpha, self.mask_src, self.mask_dst, self.reset_mask = arrays
+        else:
+            self.mask_alpha = load_float_mask(c.mask_alpha, shape, 1)
+            self.mask_src = load_bool_mask(c.mask_src, shape, True)
+            self.mask_dst = load_bool_mask(c.mask_dst, shape, True)
+            self.reset_mask = load_float_mask(c.reset_mask, shape, 1)
 
         def dev(a, dtype):
             return torch.from_numpy(np.ascontiguousarray(a.astype(dtype))).cuda()
@@ -236,7 +250,8 @@ class Layer:
         check(self._lib.tf_layer_get_counters(self._handle, C.byref(frames), C.byref(once)))
         return {"config": self.config, "height": self.height, "width": self.width, "sources": self.sources,
                 "data": data, "rgba": rgba, "frames": frames.value, "introduced_once": bool(once.value),
-                "reset_rng": self.reset_rng, "rng_seed": self.rng_seed}
+                "reset_rng": self.reset_rng, "rng_seed": self.rng_seed,
+                "masks": (self.mask_alpha, self.mask_src, self.mask_dst, self.reset_mask)}
 
     def __setstate__(self, state):
         self.config = state["config"]
@@ -246,7 +261,7 @@ class Layer:
         self._lib = _lib.load()
         self._handle = C.c_void_p()
         self._create()
-        self._upload_masks()
+        self._upload_masks(state.get("masks"))
         if self.sources:
             self._push_sources()
         d = None if state["data"] is None else torch.from_numpy(state["data"]).cuda()

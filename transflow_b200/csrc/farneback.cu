@@ -770,13 +770,18 @@ static int g_fb_two_pass = 0;  // tf_farneback_tune(1, ..): separate blur passes
 #include "fb_half.cuh"
 #include "fb_stage.cuh"
 #include "fb_tma.cuh"
+#include "fb_ring.cuh"
 
 int g_fbh_rows = 0;
 int g_fbh_rows_min_px = 0;
+int g_fbr_rows = 0;
+static int g_fbr_min_px = 1000000;  // variant 8 uses the ring kernel on levels of at least this many pixels (key 4)
 extern "C" int tf_farneback_tune(int key, int value) {
     if (key == 0) g_fbh_rows = value;
     else if (key == 1) g_fb_two_pass = value;
     else if (key == 2) g_fbh_rows_min_px = value;
+    else if (key == 3) g_fbr_rows = value;
+    else if (key == 4) g_fbr_min_px = value;
     else return fail(TF_ERR_INVALID_ARG, "tf_farneback_tune: unknown key %d", key);
     return TF_OK;
 }
@@ -1129,6 +1134,12 @@ static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int var
                                                variant - 9)
                         : fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st);
             if (e) return e;
+        } else if (variant >= 18 && variant <= 20) {
+            const bool big = (size_t)L.w * L.h >= (size_t)400000;
+            int e = big ? fb_iterate_ring<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st,
+                                              variant == 18 ? 256 : variant == 19 ? 320 : 384)
+                        : fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st);
+            if (e) return e;
         } else if (variant == 8) {
             // default: the half-buffer kernel with the 4-column phase C (variant 17) where a level gives it enough CTAs
             // (157 vs 185 us at 4K, 41 vs 52 us at 1080p, 15.1 vs 18.6 us at 960x540), the rolling-tile kernel below
@@ -1155,7 +1166,7 @@ extern "C" int tf_farneback_solve(tf_farneback* h, int slot_left, int slot_right
     TF_REQUIRE(h && flow, TF_ERR_INVALID_ARG, "tf_farneback_solve: null argument");
     TF_REQUIRE(slot_ok(slot_left) && slot_ok(slot_right) && h->has_frame[slot_left] && h->has_frame[slot_right],
                TF_ERR_INVALID_ARG, "tf_farneback_solve: slots must be prepared slots in [0, %d)", FB_SLOTS);
-    TF_REQUIRE(variant >= 0 && variant <= 17, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
+    TF_REQUIRE(variant >= 0 && variant <= 20, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
     TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_solve: flow must be 8-byte aligned");
     cudaStream_t st = as_stream(stream);
     float2* out = reinterpret_cast<float2*>(flow);
@@ -1171,7 +1182,7 @@ extern "C" int tf_farneback_step_lane(tf_farneback* h, int lane, int new_slot, c
                "tf_farneback_step: slots must be in [0, %d)", FB_SLOTS);
     TF_REQUIRE((new_slot == slot_left) != (new_slot == slot_right), TF_ERR_INVALID_ARG,
                "tf_farneback_step: the new frame must be exactly one side of the pair");
-    TF_REQUIRE(variant >= 0 && variant <= 17, TF_ERR_INVALID_ARG, "tf_farneback_step: unknown variant %d", variant);
+    TF_REQUIRE(variant >= 0 && variant <= 20, TF_ERR_INVALID_ARG, "tf_farneback_step: unknown variant %d", variant);
     TF_REQUIRE(variant != 1 || lane == 0, TF_ERR_INVALID_ARG,
                "tf_farneback_step: the unfused reference kernels (variant 1) share their scratch, lane 0 only");
     TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_step: flow must be 8-byte aligned");
