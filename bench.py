@@ -1,24 +1,31 @@
 #!/usr/bin/env python
-"""bench.py -- frames/sec at 4K for flow + accumulate + remap (BASELINE.json metric).
+"""bench.py -- frames/sec for flow + accumulate + remap (BASELINE.json metric), any BASELINE config.
 
-Workload (config C3 of SURVEY.md 8d, the configuration the metric is quoted on): synthetic
-3840x2160 clip, Farneback defaults, FORWARD direction, one `moveref` layer with random reset
-0.5 and a radial reset mask, seeded colour-noise pixmap.  One step = one frame pair through
-BGR->gray, pyramid + polynomial expansion of the new frame, the coarse-to-fine displacement
-solve, the forward post-process, and the fused move/reset/remap/composite kernel.
+  python bench.py [--config C1..C5] [--gpus N] [--steps K] [--warmup W]     our arm (CUDA, C ABI)
+  python bench.py --impl reference [...]                                     the reference's own CPU classes
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, C ABI)
-  python bench.py --impl reference [...]                          reference CPU arm (oracle: cv2 + NumPy)
+Default = config C3, the one the metric is quoted on: synthetic 3840x2160 clip, Farneback defaults, FORWARD
+direction, one `moveref` layer with random reset 0.5 and a radial reset mask.  The other configs of BASELINE.json
+ are selectable with --config:
 
-Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` goes
-through the public plugin API (FlowSource + Compositor) with pinned HOST frames in and a HOST
-RGB frame out every step.
+  C1  854x480   Farneback, backward, moveref                       (README basic transfer; River.mp4 stand-in)
+  C2  1920x1080 Horn-Schunck (alpha 1, 3 sweeps, decay 0), sum layer
+  C3  3840x2160 Farneback, forward, moveref + random reset 0.5 + reset mask
+  C4  3840x2160 pyramidal Lucas-Kanade (win 15, 3 levels, dense), static layer fed by the video + moveref -e
+                fed by an RGBA still (README sticky texture); --lk-step 4 = assets/configs/lukas-kanade.json
+  C5  7680x4320 Farneback, backward, moveref (frame pairs sharded over the ranks at N > 1)
+
+One STEP is a fixed batch of frames (`config.frames_per_step`), sized so that the driver's `--steps 20` window lasts
+about a second; `value` = steps * frames_per_step / device time, frames resident in HBM.  `e2e` runs the same number
+of frames through the public plugin API (FlowSource.from_args(...) iterated + Compositor.step) with pinned HOST
+frames in and a HOST RGB frame out every frame.  Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -27,9 +34,31 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H4K, W4K = 2160, 3840
 N_DISTINCT = 12            # distinct frames cycled (ping-pong order keeps |flow| small)
 BG = "#204060"
+METRIC = "frames/sec at 4K (flow+accumulate+remap)"
+
+CONFIGS = {
+    "C1": dict(height=480, width=854, method="farneback", direction="backward", frames_per_step=512,
+               layers=[dict(classname="moveref")],
+               what="README basic transfer stand-in: synthetic 854x480 clip, Farneback defaults, backward, moveref, "
+                    "cnoise pixmap"),
+    "C2": dict(height=1080, width=1920, method="horn-schunck", direction="backward", frames_per_step=256,
+               layers=[dict(classname="sum")],
+               what="synthetic 1080p clip, Horn-Schunck (alpha 1, 3 sweeps, decay 0, delta 1), backward, sum layer, "
+                    "cnoise pixmap"),
+    "C3": dict(height=2160, width=3840, method="farneback", direction="forward", frames_per_step=64,
+               layers=[dict(classname="moveref", reset_mode="random", reset_random_factor=0.5, reset_mask="@radial")],
+               what="synthetic 3840x2160 clip, Farneback defaults (pyr 0.5, 3 levels, win 15, 3 iters, poly 5/1.2), "
+                    "forward direction, moveref layer with random reset 0.5 + radial reset mask, cnoise pixmap"),
+    "C4": dict(height=2160, width=3840, method="lukas-kanade", direction="backward", frames_per_step=8,
+               layers=[dict(classname="static"), dict(classname="moveref", moving_pixels_leave_empty_spot=True)],
+               what="synthetic 3840x2160 clip, pyramidal Lucas-Kanade (win 15, max level 2), backward, layer 0 static "
+                    "fed by the video itself, layer 1 moveref with moving_pixels_leave_empty_spot fed by an RGBA still"),
+    "C5": dict(height=4320, width=7680, method="farneback", direction="backward", frames_per_step=16,
+               layers=[dict(classname="moveref")],
+               what="synthetic 7680x4320 stream, Farneback defaults, backward, moveref, cnoise pixmap"),
+}
 
 
 def frame_order(t: int, n: int) -> int:
@@ -45,6 +74,23 @@ def measured_peak_gbs():
         with open(path) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic(kernel_tag: str, shape):
+    """DRAM bytes per launch of a kernel from its committed `ncu --set full` capture (profiles/traffic.json), or
+    (None, None): this run does not measure DRAM traffic, it quotes the capture and says which."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.isfile(path):
+        return None, None
+    with open(path) as f:
+        table = json.load(f)
+    entry = table.get(f"{kernel_tag}@{shape[1]}x{shape[0]}")
+    if not entry:
+        return None, None
+    variant = os.environ.get("TFB200_FB_VARIANT")
+    if entry.get("variant") is not None and variant is not None and str(entry["variant"]) != variant:
+        return None, None
+    return float(entry["dram_bytes"]), entry["source"]
 
 
 class ClockSampler:
@@ -115,42 +161,208 @@ class ClockSampler:
                 "samples": len(sm), "window": self.window}
 
 
-def build_workload(height, width, n_frames, seed=0):
+# ------------------------------------------------------------------------------------------------
+# workload (shared by both arms)
+# ------------------------------------------------------------------------------------------------
+def resolve_config(args):
+    cfg = dict(CONFIGS[args.config])
+    cfg["name"] = args.config
+    if args.height:
+        cfg["height"] = args.height
+    if args.width:
+        cfg["width"] = args.width
+    if args.frames_per_step:
+        cfg["frames_per_step"] = args.frames_per_step
+    cfg["lk_step"] = args.lk_step
+    return cfg
+
+
+def cv_params(cfg) -> dict:
+    """Fields of the reference's CvFlowConfig JSON for this config (flow/sources/cv.py:273-305 defaults)."""
+    if cfg["method"] == "lukas-kanade":
+        return dict(method="lukas-kanade", lk_window_size=15, lk_max_level=2, lk_step=cfg["lk_step"])
+    if cfg["method"] == "horn-schunck":
+        return dict(method="horn-schunck", hs_alpha=1, hs_iterations=3, hs_decay=0, hs_delta=1)
+    return dict(method="farneback")
+
+
+def build_workload(cfg, n_frames, height=None, seed=0):
+    """-> clip (T, H, W, 3) BGR u8, reset mask f32 (H, W), pixmaps per layer (u8 stills; None = the video itself)."""
     from transflow_b200.synthetic import cnoise_pixmap, radial_mask, synthetic_clip
-    clip = synthetic_clip(height, width, n_frames, seed=seed)       # (T, H, W, 3) BGR uint8
-    return clip, radial_mask(height, width), cnoise_pixmap(height, width, seed + 1)
+    h, w = height or cfg["height"], cfg["width"]
+    clip = synthetic_clip(h, w, n_frames, seed=seed)
+    mask = radial_mask(h, w)
+    pixmaps = []
+    for li, layer in enumerate(cfg["layers"]):
+        if layer["classname"] == "static":
+            pixmaps.append(None)
+        elif cfg["name"] == "C4":       # RGBA still with a transparent centre (stand-in for assets/Frame.png)
+            rgba = np.concatenate([cnoise_pixmap(h, w, seed + 1 + li), np.zeros((h, w, 1), np.uint8)], axis=2)
+            rgba[..., 3] = np.where(mask > 0.45, 255, 0)
+            pixmaps.append(rgba)
+        else:
+            pixmaps.append(cnoise_pixmap(h, w, seed + 1 + li))
+    return clip, mask, pixmaps
 
 
 def write_mask_png(mask, tag):
     import PIL.Image
-    import tempfile
     path = os.path.join(tempfile.gettempdir(), f"tfb200_mask_{tag}_{os.getpid()}.png")
     PIL.Image.fromarray(np.rint(mask * 255).astype(np.uint8)).save(path)
     return path
 
 
+def layer_kwargs(cfg, mask_png):
+    out = []
+    for layer in cfg["layers"]:
+        kw = dict(layer)
+        if kw.get("reset_mask") == "@radial":
+            kw["reset_mask"] = mask_png
+        out.append(kw)
+    return out
+
+
+def workload_config(cfg, extra=None):
+    h, w = cfg["height"], cfg["width"]
+    d = {"workload": f"{cfg['name']}: {cfg['what']}" + (f" [size overridden: {w}x{h}]"
+                                                        if (h, w) != (CONFIGS[cfg['name']]['height'],
+                                                                      CONFIGS[cfg['name']]['width']) else ""),
+         "frames_per_step": cfg["frames_per_step"], "frames_cycled": N_DISTINCT,
+         "cache": "inputs larger than L2: the per-frame working set (R pyramids, data ping-pong, flows; > 1 GB at 4K) "
+                  "exceeds the 126 MB L2 and 12 distinct frames are cycled; no explicit flush",
+         "reset_rng": "device Philox (throughput mode)"}
+    if cfg["method"] == "farneback":
+        d["farneback_variant"] = os.environ.get("TFB200_FB_VARIANT", "default")
+        d["pairs_in_flight"] = max(1, min(2, int(os.environ.get("TFB200_FB_LANES", "2"))))
+    if cfg["method"] == "lukas-kanade":
+        d["lk_step"] = cfg["lk_step"]
+    if extra:
+        d.update(extra)
+    return d
+
+
+def algorithmic_bytes_per_frame(cfg, fb=None) -> float:
+    """SURVEY.md 8(d) / DESIGN.md 4: dependency-respecting minimum HBM bytes of one frame of this config."""
+    n = float(cfg["height"] * cfg["width"])
+    forward = cfg["direction"] == "forward"
+    if cfg["method"] == "farneback":
+        flow = fb.algorithmic_bytes(True) + n * 3.0 + n      # + BGR frame read, gray write
+    elif cfg["method"] == "horn-schunck":
+        flow = 98.0 * n + 4.0 * n
+    else:
+        flow = 2.0 * 1.3125 * n + 16.0 * 3.0 * n / (cfg["lk_step"] ** 2) + 4.0 * n
+    post = 24.0 * n if forward else 16.0 * n                 # backward: clip pass reads + writes the flow
+    comp = 0.0
+    for layer in cfg["layers"]:
+        kind = layer["classname"]
+        comp += {"moveref": 46.0, "sum": 30.0, "static": 6.0}[kind] * n
+        if layer.get("reset_mask"):
+            comp += 4.0 * n
+    return flow + post + comp
+
+
 # ------------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU path (cv2 Farneback call site + NumPy compositor), oracle port
+# reference arm: the reference's OWN classes (baseline/_ref, installed from /root/reference) on the host cores
 # ------------------------------------------------------------------------------------------------
-def reference_step_fn(clip, mask, pixmap):
-    """Returns step(t) running one frame of the reference CPU pipeline on the given frames."""
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REF_DIR, "transflow", "pipeline.py"))
+
+
+class _FakeQueue:
+    """Stands in for the multiprocessing.Queue a pixmap SourceProcess feeds (one copy per get, like unpickling)."""
+
+    def __init__(self, frames, cycle=False):
+        self.frames, self.cycle, self.i = frames, cycle, 0
+
+    def get(self, timeout=None):
+        i = frame_order(self.i, len(self.frames)) if self.cycle else min(self.i, len(self.frames) - 1)
+        self.i += 1
+        return np.array(self.frames[i])
+
+
+def reference_step_fn(cfg, hs, n_frames, tmp):
+    """-> (step(), kind): one frame through the reference's CPU path on a band of `hs` rows.
+
+    kind "reference": the unmodified reference classes -- `FlowSource.from_args(<FFV1 clip>, cv_config=<json>,
+    direction=...)` iterated (CvFlowSource: decode, resize, BGR2GRAY, cv2 / NumPy flow, post_process) then
+    `Compositor.update(flow)` + `Compositor.render()` with in-process stand-ins for the pixmap queues, single process,
+    as SURVEY.md 8(d) specifies.  kind "port": baseline/_ref is absent -> the oracle restatement of the same calls."""
+    import cv2
+    band = dict(cfg, height=hs)
+    clip, mask, pixmaps = build_workload(band, min(n_frames, N_DISTINCT), height=hs)
+    mask_png = write_mask_png(mask, "ref")
+    w = cfg["width"]
+    if not reference_available():
+        return _port_step_fn(cfg, clip, mask, pixmaps), "port"
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REF_DIR)
+    from transflow.compositor.compositor import Compositor
+    from transflow.compositor.pixmap_source_interface import PixmapSourceInterface
+    from transflow.config import LayerConfig
+    from transflow.flow.sources.source import FlowSource
+    avi = os.path.join(tmp, "clip.avi")
+    vw = cv2.VideoWriter(avi, cv2.VideoWriter_fourcc(*"FFV1"), 25, (w, hs))
+    if not vw.isOpened():
+        raise RuntimeError("cv2 cannot write FFV1")
+    for t in range(n_frames):
+        vw.write(clip[frame_order(t, len(clip))])
+    vw.release()
+    cfg_json = os.path.join(tmp, "cv.json")
+    with open(cfg_json, "w") as fp:
+        json.dump(cv_params(cfg), fp)
+    builder = FlowSource.from_args(avi, cv_config=cfg_json, direction=cfg["direction"])
+    source = builder.__enter__()          # (includes the one-off FlowSource.__init__ index arrays: not timed)
+    layers = [LayerConfig(i, **kw) for i, kw in enumerate(layer_kwargs(cfg, mask_png))]
+    comp = Compositor.from_args(hs, w, layers, background_color=BG)
+    everywhere = np.ones((hs, w), bool)
+    rgb_video = [np.ascontiguousarray(f[..., ::-1]) for f in clip]
+    comp.set_sources({i: [PixmapSourceInterface(_FakeQueue(rgb_video, cycle=True) if p is None else _FakeQueue([p]),
+                                                 everywhere)] for i, p in enumerate(pixmaps)})
+    it = iter(source)
+
+    def step():
+        flow = next(it)
+        comp.update(flow)
+        return comp.render()
+    return step, "reference"
+
+
+def _port_step_fn(cfg, clip, mask, pixmaps):
     import cv2
     from oracle import compositor_np as CN
     from oracle import flow_cv as F
     h, w = clip.shape[1:3]
-    layer = CN.LayerOracle(CN.LayerSpec(classname="moveref", reset_mode="random", reset_random_factor=0.5), h, w,
-                           intro_masks=[np.ones((h, w), bool)], reset_mask=mask)
+    forward = cfg["direction"] == "forward"
+    everywhere = np.ones((h, w), bool)
+    layers = []
+    for kw in cfg["layers"]:
+        spec = {k: v for k, v in kw.items() if k != "reset_mask"}
+        layers.append(CN.LayerOracle(CN.LayerSpec(**spec), h, w, intro_masks=[everywhere],
+                                     reset_mask=mask if kw.get("reset_mask") else None))
     bg = np.empty((h, w, 3), np.uint8)
     bg[:, :] = (0x20, 0x40, 0x60)
-    state = {"prev": cv2.cvtColor(clip[0], cv2.COLOR_BGR2GRAY)}
+    state = {"prev": cv2.cvtColor(clip[0], cv2.COLOR_BGR2GRAY), "t": 0}
+    p = cv_params(cfg)
 
-    def step(t):
-        gray = cv2.cvtColor(clip[frame_order(t + 1, len(clip))], cv2.COLOR_BGR2GRAY)
-        flow = F.farneback(state["prev"], gray)                       # forward: (prev, cur)
-        flow = F.post_process(flow, True)
-        layer.update(flow, [pixmap])
-        out = CN.composite(bg, [layer.render()])
-        state["prev"] = gray
+    def step():
+        t = state["t"]
+        frame = clip[frame_order(t + 1, len(clip))]
+        gray = cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)
+        left, right = (state["prev"], gray) if forward else (gray, state["prev"])
+        if cfg["method"] == "farneback":
+            flow = F.farneback(left, right)
+        elif cfg["method"] == "horn-schunck":
+            flow = F.horn_schunck(left, right, None, p["hs_alpha"], p["hs_iterations"], p["hs_decay"], p["hs_delta"])
+        else:
+            flow = F.lukas_kanade(left, right, p["lk_window_size"], p["lk_max_level"], p["lk_step"])
+        flow = F.post_process(flow, forward)
+        for layer, pm in zip(layers, pixmaps):
+            layer.update(flow, [np.ascontiguousarray(frame[..., ::-1]) if pm is None else pm])
+        out = CN.composite(bg, [layer.render() for layer in layers])
+        state["prev"], state["t"] = gray, t + 1
         return out
     return step
 
@@ -160,34 +372,47 @@ def cpu_threads():
     return max(int(cv2.getNumThreads()), 1)
 
 
+#: rough seconds of reference CPU work per full frame, only used to size the bounded sample
+_REF_SECONDS_PER_FRAME = {"C1": 0.45, "C2": 2.5, "C3": 10.0, "C4": 7.0, "C5": 40.0}
+
+
+def _band_rows(cfg, seconds_per_step):
+    frac = min(1.0, seconds_per_step / _REF_SECONDS_PER_FRAME[cfg["name"]])
+    return int(min(cfg["height"], max(136, round(cfg["height"] * frac / 8) * 8)))
+
+
+def _sample_text(cfg, n, hs, kind):
+    w, h = cfg["width"], cfg["height"]
+    who = ("the unmodified reference classes from baseline/_ref (CvFlowSource via FlowSource.from_args on an FFV1 clip, "
+           "Compositor.update + render)" if kind == "reference" else "the oracle port of the reference's calls")
+    return (f"{n} frames of a {w}x{hs} band ({hs / h:.3f} of a {w}x{h} frame) through {who}, single process, value "
+            f"scaled by that fraction; cv2 threads = {cpu_threads()} (cv2 Farneback itself runs on ~1 core)")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    cfg = resolve_config(args)
     total = args.steps + args.warmup
-    # bounded sample: a full 4K frame costs ~6 s on the CPU path; shrink the band of rows so the
-    # whole run stays within ~150 s, and scale the result back to 4K-frame equivalents
-    per_step_budget = 150.0 / max(total, 1)
-    frac = min(1.0, per_step_budget / 6.0)
-    hs = int(min(args.height, max(136, round(args.height * frac / 8) * 8)))
-    clip, mask, pixmap = build_workload(hs, args.width, 4, seed=0)
-    step = reference_step_fn(clip, mask, pixmap)
-    for t in range(args.warmup):
-        step(t)
-    t0 = time.perf_counter()
-    for t in range(args.warmup, total):
-        step(t)
-    dt = time.perf_counter() - t0
-    scale = hs / args.height
+    hs = _band_rows(cfg, 150.0 / max(total, 1))
+    with tempfile.TemporaryDirectory() as tmp:
+        step, kind = reference_step_fn(cfg, hs, total + 2, tmp)
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = time.perf_counter() - t0
+    scale = hs / cfg["height"]
     fps = args.steps / dt * scale
-    sample = (f"{args.steps} frames of a {args.width}x{hs} band ({scale:.3f} of a {args.width}x{args.height} frame), "
-              f"value scaled by that fraction; cv2.calcOpticalFlowFarneback + NumPy post-process + NumPy moveref")
     line = {
-        "impl": "reference", "metric": "frames/sec at 4K (flow+accumulate+remap)", "value": fps, "unit": "frames/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps / scale,
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps / scale,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cpu_threads(), "kind": "port", "sample": sample},
+        "config": workload_config(cfg),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cpu_threads(), "kind": kind,
+                         "sample": _sample_text(cfg, args.steps, hs, kind)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -195,106 +420,180 @@ def run_reference(args):
     return 0
 
 
-def workload_config(args):
-    return {"workload": f"C3: synthetic {args.width}x{args.height} clip, Farneback defaults (pyr 0.5, 3 levels, win 15, "
-                        "3 iters, poly 5/1.2), forward direction, moveref layer with random reset 0.5 + radial reset "
-                        "mask, cnoise pixmap",
-            "frames_cycled": N_DISTINCT,
-            "cache": "working set per frame (R pyramids 2x220 MB, data 2x133 MB, flow 66 MB at 4K) exceeds the 126 MB L2; "
-                     "no explicit flush",
-            "reset_rng": "device Philox (throughput mode)",
-            "farneback_variant": os.environ.get("TFB200_FB_VARIANT", "default"),
-            "pairs_in_flight": max(1, min(2, int(os.environ.get("TFB200_FB_LANES", "2"))))}
-
-
-# ------------------------------------------------------------------------------------------------
-# our arm
-# ------------------------------------------------------------------------------------------------
-def cpu_baseline_sample(args):
-    """Oracle timed on this box's host cores on a bounded sample (about 10-30 s of CPU work)."""
-    hs = min(args.height, 1080)
-    clip, mask, pixmap = build_workload(hs, args.width, 3, seed=0)
-    step = reference_step_fn(clip, mask, pixmap)
-    step(0)
-    t0 = time.perf_counter()
+def cpu_baseline_sample(cfg):
+    """The reference CPU path timed on this box's host cores on a bounded sample (about 10-30 s of CPU work)."""
     n = 2
-    for t in range(1, 1 + n):
-        step(t)
-    dt = time.perf_counter() - t0
-    scale = hs / args.height
-    return {"value": n / dt * scale, "unit": "frames/s", "cores": cpu_threads(), "kind": "port",
-            "sample": f"{n} frames of a {args.width}x{hs} band ({scale:.3f} of a frame) through cv2 Farneback + NumPy "
-                      "post-process + NumPy moveref oracle, scaled to full frames; cv2 Farneback is effectively "
-                      "single-threaded"}
+    hs = _band_rows(cfg, 6.0)
+    with tempfile.TemporaryDirectory() as tmp:
+        step, kind = reference_step_fn(cfg, hs, n + 3, tmp)
+        step()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            step()
+        dt = time.perf_counter() - t0
+    scale = hs / cfg["height"]
+    return {"value": n / dt * scale, "unit": "frames/s", "cores": cpu_threads(), "kind": kind,
+            "sample": _sample_text(cfg, n, hs, kind)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm: device-resident workload
+# ------------------------------------------------------------------------------------------------
+class _CyclingQueue:
+    """Pixmap queue of a video source that plays the clip itself: frame t + 1 at step t (cycled like the flow)."""
+
+    def __init__(self, frames, first=1):
+        self.frames, self.i = frames, first
+
+    def get(self, timeout=None):
+        f = self.frames[frame_order(self.i, len(self.frames))]
+        self.i += 1
+        return f
+
+
+def make_compositor(cfg, mask_png, pixmaps, video_frames_rgb, to_device=True):
+    """Compositor of the config with its pixmap interfaces; `video_frames_rgb` feeds the layers whose pixmap is the
+    video itself (C4's static layer)."""
+    import torch
+    from transflow_b200.compositor import Compositor
+    from transflow_b200.compositor.pixmap_source_interface import PixmapSourceInterface, StillQueue
+    from transflow_b200.config import LayerConfig
+    h, w = cfg["height"], cfg["width"]
+    comp = Compositor.from_args(h, w, [LayerConfig(i, **kw) for i, kw in enumerate(layer_kwargs(cfg, mask_png))],
+                                background_color=BG, seed=0)
+    everywhere = np.ones((h, w), bool)
+    sources = {}
+    for i, p in enumerate(pixmaps):
+        if p is None:
+            q = _CyclingQueue(video_frames_rgb)
+        else:
+            q = StillQueue(torch.from_numpy(p).cuda() if to_device else p)
+        sources[i] = [PixmapSourceInterface(q, everywhere)]
+    comp.set_sources(sources)
+    return comp
+
+
+class Estimator:
+    """Flow of pair (t, t + 1) of the device-resident clip for one config: gray conversion + the method's engine.
+    Farneback keeps two pairs in flight on the handle's lanes; frame t lives in slot t % 3."""
+
+    def __init__(self, cfg, frames_dev, lanes):
+        import torch
+        from transflow_b200 import ops
+        self.cfg, self.frames, self.ops = cfg, frames_dev, ops
+        h, w = cfg["height"], cfg["width"]
+        self.forward = cfg["direction"] == "forward"
+        self.method = cfg["method"]
+        self.lanes = lanes if self.method == "farneback" else 1
+        self.nslots = 3 if self.lanes > 1 else 2
+        variant = int(os.environ.get("TFB200_FB_VARIANT", "-1"))
+        if self.method == "farneback":
+            self.engine = (ops.Farneback(h, w, lanes=self.lanes) if variant < 0
+                           else ops.Farneback(h, w, variant=variant, lanes=self.lanes))
+            self.grays = [torch.empty((h, w), dtype=torch.uint8, device="cuda") for _ in range(self.lanes)]
+        else:
+            p = cv_params(cfg)
+            self.engine = (ops.HornSchunck(h, w) if self.method == "horn-schunck"
+                           else ops.LucasKanade(h, w, p["lk_window_size"], p["lk_max_level"], p["lk_step"]))
+            self.params = p
+            self.grays = [torch.empty((h, w), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        self.n = 0      # pairs submitted since begin()
+
+    def frame(self, idx):
+        return self.frames[frame_order(idx, len(self.frames))]
+
+    def begin(self, first_frame, frame_fn=None):
+        """(Re)start at `first_frame`: its gray image (+ pyramid / expansion for Farneback) is built here."""
+        self.frame_fn = frame_fn or self.frame
+        self.n = 0
+        g = self.ops.gray_from_bgr(self.frame_fn(first_frame), self.grays[0])
+        if self.method == "farneback":
+            self.engine.prepare(0, g)
+
+    def pair(self, next_frame, out, lane=0):
+        """Flow of (previous frame, `next_frame`) into `out`, on the current stream."""
+        n = self.n
+        self.n = n + 1
+        if self.method == "farneback":
+            old, new = n % self.nslots, (n + 1) % self.nslots
+            g = self.ops.gray_from_bgr(self.frame_fn(next_frame), self.grays[lane])
+            left, right = (old, new) if self.forward else (new, old)
+            return self.engine.step(new, g, left, right, out, lane=lane)
+        prev, cur = self.grays[n & 1], self.grays[(n + 1) & 1]
+        self.ops.gray_from_bgr(self.frame_fn(next_frame), cur)
+        left, right = (prev, cur) if self.forward else (cur, prev)
+        if self.method == "horn-schunck":
+            p = self.params
+            return self.engine(left, right, None, p["hs_alpha"], p["hs_iterations"], p["hs_decay"], p["hs_delta"],
+                               out=out)
+        return self.engine(left, right, out=out)
+
+
+ROOFLINE_KERNELS = {
+    # method -> (timer tag, algorithmic bytes per launch as a function of (n_px, lk_step), note)
+    "farneback": ("fb_iter_finest", lambda n, s: 56.0 * n, None),
+    "horn-schunck": ("hs_sweep", lambda n, s: 28.0 * n, None),
+    "lukas-kanade": ("lk_track_finest", lambda n, s: 6.0 * n + 16.0 * n / (s * s),
+                     "the tracker is bound by integer ALU / shared-memory throughput, not HBM (SURVEY.md 8d): the HBM "
+                     "fraction is reported because the contract asks for it, not as the kernel's ceiling"),
+}
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from transflow_b200 import _lib, ops
-    from transflow_b200.compositor import Compositor
-    from transflow_b200.compositor.pixmap_source_interface import PixmapSourceInterface, StillQueue
-    from transflow_b200.config import LayerConfig
-    from transflow_b200.flow import FlowSource
-    from transflow_b200.flow.sources.cv import ArrayCapture, CvFlowConfig
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    cfg = resolve_config(args)
     if world > 1:
         # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout carries one JSON line only
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if world > 1:
-        from transflow_b200 import distributed as tfd
-        return tfd.bench_sharded(args, rank, world, local)
+        return run_sharded(args, cfg, rank, world, local)
 
-    H, W = args.height, args.width
-    clip, mask, pixmap = build_workload(H, W, N_DISTINCT, seed=0)
+    H, W = cfg["height"], cfg["width"]
+    FPS = cfg["frames_per_step"]
+    clip, mask, pixmaps = build_workload(cfg, N_DISTINCT)
     mask_png = write_mask_png(mask, "bench")
-    variant = int(os.environ.get("TFB200_FB_VARIANT", "-1"))
-    layer_cfg = dict(classname="moveref", reset_mode="random", reset_random_factor=0.5, reset_mask=mask_png)
+    forward = cfg["direction"] == "forward"
 
     # ---- device-resident throughput (`value`) -------------------------------------------------
     frames_dev = torch.from_numpy(clip).cuda()
-    pix_dev = torch.from_numpy(pixmap).cuda()
-    fb = ops.Farneback(H, W) if variant < 0 else ops.Farneback(H, W, variant=variant)
-    post = ops.PostProcess(H, W, forward=True)
-    comp = Compositor.from_args(H, W, [LayerConfig(0, **layer_cfg)], background_color=BG)
-    comp.set_sources({0: [PixmapSourceInterface(StillQueue(pix_dev), np.ones((H, W), bool))]})
-    rgb = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
-    # Streams, like the reference's processes (flow SourceProcess -> queue -> compositor main loop,
-    # pipeline.py:326-327): the caller's stream post-processes and composites pair t while the flow streams estimate
-    # the next pairs.  With two LANES (default) pairs t+1 and t+2 are in flight on two flow streams (frame t in
-    # handle slot t % 3, pair t on lane t % 2; every frame is still prepared once): the second pair fills the SMs
-    # the first leaves idle.  A ring of flow buffers decouples the lanes from the compositor; events order them.
+    video_rgb = frames_dev.flip(-1).contiguous() if any(p is None for p in pixmaps) else None
     lanes = max(1, min(2, int(os.environ.get("TFB200_FB_LANES", "2"))))
     pipelined = os.environ.get("TFB200_BENCH_STREAMS", "2") != "1"
     if not pipelined:
         lanes = 1
+    est = Estimator(cfg, frames_dev, lanes)
+    lanes = est.lanes
+    post = ops.PostProcess(H, W, forward=forward)
+    comp = make_compositor(cfg, mask_png, pixmaps, video_rgb)
+    rgb = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
+    # Streams, like the reference's processes (flow SourceProcess -> queue -> compositor main loop,
+    # pipeline.py:326-327): the caller's stream post-processes and composites pair t while the flow stream(s) estimate
+    # the next pair(s).  Farneback keeps two pairs in flight (handle lanes, one stream each); a ring of flow buffers
+    # decouples the estimation from the compositor; events order them.
     NB = 2 * lanes
     flows = [torch.empty((H, W, 2), dtype=torch.float32, device="cuda") for _ in range(NB)]
-    grays = [torch.empty((H, W), dtype=torch.uint8, device="cuda") for _ in range(lanes)]
     flow_streams = [torch.cuda.Stream() if pipelined else torch.cuda.current_stream() for _ in range(lanes)]
     ev_ready = [torch.cuda.Event() for _ in range(NB)]
     ev_free = [torch.cuda.Event() for _ in range(NB)]
-    fb.prepare(0, ops.gray_from_bgr(frames_dev[0], grays[0]))
+    est.begin(0)
     torch.cuda.synchronize()
-    nslots = 3 if lanes > 1 else 2
 
     def step(t, serial=False):
         lane = t % lanes
-        old, new = t % nslots, (t + 1) % nslots
         k = t % NB
         main = torch.cuda.current_stream()
         with torch.cuda.stream(flow_streams[lane]):
             if pipelined:
-                flow_streams[lane].wait_event(ev_free[k])  # the compositor is done with this buffer (NB steps ago)
-            ops.gray_from_bgr(frames_dev[frame_order(t + 1, N_DISTINCT)], grays[lane])
-            # prepare(new) overlapped with solve(old, new): forward direction
-            fb.step(new, grays[lane], old, new, flows[k], lane=lane)
+                flow_streams[lane].wait_event(ev_free[k])  # the compositor is done with this buffer (NB frames ago)
+            est.pair(t + 1, flows[k], lane=lane)
             if pipelined:
                 ev_ready[k].record(flow_streams[lane])
         if pipelined:
@@ -303,54 +602,54 @@ def run_ours(args):
         comp.step(flows[k], rgb)
         if pipelined:
             ev_free[k].record(main)
-            if serial:      # kernel-alone pass: nothing of step t+1 may overlap step t
+            if serial:      # kernel-alone pass: nothing of frame t+1 may overlap frame t
                 for fs in flow_streams:
                     fs.wait_event(ev_free[k])
 
     sampler = ClockSampler(local)
     sampler.start()             # running before the warm-up, so that its first samples are not lost to start-up
-    for t in range(args.warmup):
+    t = 0
+    for _ in range(args.warmup * FPS):
         step(t)
+        t += 1
     torch.cuda.synchronize()
     sampler.mark_begin()
     _lib.timer_enable(True)
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for t in range(args.warmup, args.warmup + args.steps):
+    for _ in range(args.steps * FPS):
         step(t)
+        t += 1
     e1.record()
     torch.cuda.synchronize()
     sampler.mark_end()
     ms = e0.elapsed_time(e1)
+    n_frames = args.steps * FPS
     launches = _lib.launch_count() - launches0
     kernel_ms = {tag: _lib.timer_read(tag) for tag in _lib.KERNEL_TAGS}
     _lib.timer_enable(False)
     if sampler.samples_in_window() < 2:
-        t_extra = [args.warmup + args.steps]
-
         def keep_busy():
-            for _ in range(20):
-                step(t_extra[0])
-                t_extra[0] += 1
+            nonlocal t
+            for _ in range(max(4, min(FPS, 32))):
+                step(t)
+                t += 1
             torch.cuda.synchronize()
         sampler.extend(keep_busy)
-        t_after = t_extra[0]
-    else:
-        t_after = args.warmup + args.steps
     clocks = sampler.stop()
-    fps = args.steps / (ms / 1000.0)
+    fps = n_frames / (ms / 1000.0)
     # With two lanes a kernel's event-bracketed duration in the timed region includes the kernels of the other
     # pair it shares the SMs with.  The roofline of the kernel ITSELF is taken from a second, serialised pass of
-    # the same steps (every step waits for the previous one: the ncu launch list's condition); both are reported.
+    # the same frames (every frame waits for the previous one: the ncu launch list's condition); both are reported.
     kernel_ms_region = kernel_ms
-    if lanes > 1:
-        n_serial = max(20, min(args.steps, 100))
+    if pipelined:
+        n_serial = max(8, min(n_frames, 64))
         torch.cuda.synchronize()
         _lib.timer_enable(True)
-        t_next = t_after
-        for t in range(t_next, t_next + n_serial):
+        for _ in range(n_serial):
             step(t, serial=True)
+            t += 1
         torch.cuda.synchronize()
         kernel_ms = {tag: _lib.timer_read(tag) for tag in _lib.KERNEL_TAGS}
         _lib.timer_enable(False)
@@ -358,47 +657,43 @@ def run_ours(args):
     # ---- roofline of the dominant kernel --------------------------------------------------------
     peak, peak_src = measured_peak_gbs()
     n_px = H * W
-    # algorithmic bytes per launch: fused iteration = 56 B/px; unfused kernels: their own traffic
-    alg = {"fb_iter_finest": 56.0 * n_px, "fb_um_finest": 68.0 * n_px, "fb_boxv_finest": 60.0 * n_px,
-           "fb_boxh_finest": 48.0 * n_px}
-    cand = {k: v for k, v in kernel_ms.items() if k in alg and v[1] > 0}
-    dom = max(cand, key=lambda k: cand[k][0]) if cand else None
+    tag, alg_fn, note = ROOFLINE_KERNELS[cfg["method"]]
+    alg = alg_fn(float(n_px), cfg["lk_step"])
     roofline = None
-    if dom:
-        tot_ms, n = cand[dom]
-        achieved = alg[dom] / (tot_ms / n / 1000.0) / 1e9
-        # DRAM traffic of the same kernel from the committed ncu --set full capture
-        # (profiles/r01_ncu_full_k_fb_iter_half_c4.txt: 453.52 MB read + 46.27 MB written per 4K launch of the
-        # default kernel; the rolling-tile kernel, TFB200_FB_VARIANT=3, moved 428.36 + 58.62 MB)
-        default_kernel = os.environ.get("TFB200_FB_VARIANT", "8") == "8"
-        traffic = None
-        if dom == "fb_iter_finest" and (H, W) == (H4K, W4K):
-            traffic = 499.80e6 if default_kernel else (486.99e6 if os.environ.get("TFB200_FB_VARIANT") == "3" else None)
-        reg_ms, reg_n = kernel_ms_region[dom]
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "avg_launch_ms": tot_ms / n, "launches": n, "share_of_step": reg_ms / ms,
-                    "algorithmic_bytes_per_launch": alg[dom],
+    if kernel_ms.get(tag, (0, 0))[1] > 0:
+        tot_ms, n = kernel_ms[tag]
+        reg_ms, reg_n = kernel_ms_region[tag]
+        achieved = alg / (tot_ms / n / 1000.0) / 1e9
+        traffic, traffic_src = profiled_traffic(tag, (H, W))
+        roofline = {"bound": "hbm", "kernel": tag, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peak_src, "avg_launch_ms": tot_ms / n, "launches": n,
+                    "share_of_step": reg_ms / ms, "algorithmic_bytes_per_launch": alg,
                     "timing": ("CUDA events around each launch on its stream; serialised pass after the timed region "
-                               "(one pair at a time), because in the timed region two pairs share the SMs"
-                               if lanes > 1 else "CUDA events around each launch on its stream, timed region"),
+                               "(one frame at a time), because in the timed region neighbouring frames share the SMs"
+                               if pipelined else "CUDA events around each launch on its stream, timed region"),
                     "in_timed_region": {"avg_launch_ms": reg_ms / max(reg_n, 1), "launches": reg_n,
-                                        "achieved": alg[dom] / (reg_ms / max(reg_n, 1) / 1000.0) / 1e9,
-                                        "frac": alg[dom] / (reg_ms / max(reg_n, 1) / 1000.0) / 1e9 / peak}}
-    frame_bytes = fb.algorithmic_bytes(True) + (24.0 + 50.0) * n_px + 3.0 * n_px + n_px
+                                        "achieved": alg / (reg_ms / max(reg_n, 1) / 1000.0) / 1e9,
+                                        "frac": alg / (reg_ms / max(reg_n, 1) / 1000.0) / 1e9 / peak}}
+        if note:
+            roofline["note"] = note
+    frame_bytes = algorithmic_bytes_per_frame(cfg, est.engine if cfg["method"] == "farneback" else None)
     pipeline_frac = frame_bytes * fps / 1e9 / peak
 
     # ---- end to end through the public plugin API with HOST frames --------------------------------
-    e2e = run_e2e(args, clip, pixmap, layer_cfg)
+    del est, comp, flows, frames_dev
+    torch.cuda.empty_cache()
+    e2e = run_e2e(args, cfg, clip, pixmaps, mask_png)
 
-    cpu = cpu_baseline_sample(args)
+    cpu = cpu_baseline_sample(cfg)
     line = {
-        "metric": "frames/sec at 4K (flow+accumulate+remap)", "value": fps, "unit": "frames/s", "n_gpus": 1,
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(cfg),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "frames_timed": n_frames, "ms_per_frame": ms / n_frames,
         "pipeline_hbm_frac": pipeline_frac, "pipeline_algorithmic_bytes_per_frame": frame_bytes,
-        "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kernel_ms_region.items() if v[1] > 0},
+        "kernel_ms_per_frame": {k: v[0] / n_frames for k, v in kernel_ms_region.items() if v[1] > 0},
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -432,34 +727,45 @@ class CyclingCapture:
         pass
 
 
-def run_e2e(args, clip, pixmap, layer_cfg):
-    """The call a user makes: FlowSource.from_args(...) iterated, Compositor.step(flow), frame read
-    back to the host.  Every step copies that step's BGR frame H2D (from pinned memory) and the RGB
-    result D2H."""
+E2E_LOOKAHEAD = 4      # frames the source may still run ahead when the clock stops
+
+
+def run_e2e(args, cfg, clip, pixmaps, mask_png):
+    """The call a user makes: FlowSource.from_args(...) iterated, Compositor.step(flow), frame read back to the
+    host.  Every frame copies that frame's BGR image H2D (from pinned memory, into the source's preallocated device
+    ring) and the RGB result D2H.  The clock runs between two device synchronisations over exactly
+    steps * frames_per_step frames in the steady state: the source is in its look-ahead regime at BOTH ends (the
+    capture holds E2E_LOOKAHEAD more frames than are timed), so no frame whose flow was computed before the clock
+    started is counted without an equal amount of look-ahead work inside the window."""
     import torch
-    from transflow_b200.compositor import Compositor
-    from transflow_b200.compositor.pixmap_source_interface import PixmapSourceInterface, StillQueue
-    from transflow_b200.config import LayerConfig
     from transflow_b200.flow import FlowSource
     from transflow_b200.flow.sources.cv import CvFlowConfig
-    H, W = args.height, args.width
+    H, W = cfg["height"], cfg["width"]
+    FPS = cfg["frames_per_step"]
+    n_warm, n_timed = max(args.warmup * FPS, 8), args.steps * FPS
     frames_pinned = torch.from_numpy(clip).pin_memory()
-    total = args.warmup + args.steps + 1
-    cap = CyclingCapture(frames_pinned, total)
-    comp = Compositor.from_args(H, W, [LayerConfig(0, **layer_cfg)], background_color=BG)
-    comp.set_sources({0: [PixmapSourceInterface(StillQueue(torch.from_numpy(pixmap).cuda()), np.ones((H, W), bool))]})
+    video_rgb = None
+    if any(p is None for p in pixmaps):
+        video_rgb = torch.from_numpy(np.ascontiguousarray(clip[..., ::-1])).pin_memory()
+    cap = CyclingCapture(frames_pinned, n_warm + n_timed + 1 + E2E_LOOKAHEAD)
+    comp = make_compositor(cfg, mask_png, pixmaps, video_rgb)
     out_ring = [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
     dev_ring = [torch.empty((H, W, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
     down = torch.cuda.Stream()
     done = [None, None]
     checksum = 0
-    with FlowSource.from_args(cap, cv_config=CvFlowConfig(), direction="forward") as src:
+    p = cv_params(cfg)
+    with FlowSource.from_args(cap, cv_config=CvFlowConfig(**p), direction=cfg["direction"]) as src:
         src.output = "device"
-        t0 = None
+        t0 = dt = None
         for i, flow in enumerate(src):
-            if i == args.warmup:
+            if i == n_warm:
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
+            if i == n_warm + n_timed:
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                break
             k = i & 1
             if done[k] is not None:
                 done[k].synchronize()
@@ -472,22 +778,342 @@ def run_e2e(args, clip, pixmap, layer_cfg):
                 out_ring[k].copy_(frame, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(down)
-            done[k] = ev
+            done[k] = ev          # (dev_ring[k] is rewritten two frames later, after done[k].synchronize() above)
+        if dt is None:
+            raise RuntimeError("the capture ended before the timed frames were done")
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-    return {"value": args.steps / dt, "unit": "frames/s", "h2d_bytes_per_step": int(H * W * 3),
-            "d2h_bytes_per_step": int(H * W * 3), "timing": "wall clock between device synchronisations",
+    h2d = H * W * 3 * (2 if video_rgb is not None else 1)
+    return {"value": n_timed / dt, "unit": "frames/s", "h2d_bytes_per_step": int(h2d * FPS),
+            "d2h_bytes_per_step": int(H * W * 3 * FPS), "frames_timed": n_timed,
+            "timing": "wall clock between device synchronisations, steady state at both ends",
             "api": "FlowSource.from_args(capture).__next__ + Compositor.step + pinned D2H"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm, N > 1: frame pairs sharded over the ranks, accumulate + remap on rank 0
+# ------------------------------------------------------------------------------------------------
+class HostFrameFeeder:
+    """Pinned host clip -> device frames through a side stream with one frame of look-ahead, into a preallocated
+    ring of device frames (a slot is rewritten once its consumer's event has passed)."""
+
+    def __init__(self, frames_pinned, order_fn, depth=4):
+        import torch
+        self.torch = torch
+        self.frames, self.order = frames_pinned, order_fn
+        self.stream = torch.cuda.Stream()
+        self.ring = [torch.empty(tuple(frames_pinned.shape[1:]), dtype=torch.uint8, device="cuda") for _ in range(depth)]
+        self.used = [None] * depth
+        self.next_slot = 0
+        self.cache = {}
+
+    def _start(self, idx):
+        if idx in self.cache:
+            return
+        torch = self.torch
+        slot = self.next_slot
+        self.next_slot = (slot + 1) % len(self.ring)
+        with torch.cuda.stream(self.stream):
+            if self.used[slot] is not None:
+                self.stream.wait_event(self.used[slot])
+            self.ring[slot].copy_(self.frames[self.order(idx)], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.cache[idx] = (slot, ev)
+
+    def get(self, idx):
+        """Device frame `idx`, valid for the kernels queued on the current stream until `release` is called."""
+        self._start(idx)
+        slot, ev = self.cache.pop(idx)
+        for stale in list(self.cache):
+            if stale != idx + 1:
+                del self.cache[stale]
+        self._start(idx + 1)
+        self.torch.cuda.current_stream().wait_event(ev)
+        self._last = slot
+        return self.ring[slot]
+
+    def release(self):
+        """The consumer of the last frame handed out has been queued on the current stream."""
+        ev = self.torch.cuda.Event()
+        ev.record()
+        self.used[self._last] = ev
+
+
+def run_sharded(args, cfg, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    from transflow_b200 import _lib, ops
+    from transflow_b200.distributed import ShardedFlowStream, plan_round
+
+    H, W = cfg["height"], cfg["width"]
+    K, Q = 8, 4
+    clip, mask, pixmaps = build_workload(cfg, N_DISTINCT)
+    forward = cfg["direction"] == "forward"
+    frames_dev = torch.from_numpy(clip).cuda()
+    feeder = HostFrameFeeder(torch.from_numpy(clip).pin_memory(), lambda i: frame_order(i, N_DISTINCT))
+    io = {"host": False}
+
+    def frame(idx):
+        return feeder.get(idx) if io["host"] else frames_dev[frame_order(idx, N_DISTINCT)]
+
+    lanes_req = max(1, min(2, int(os.environ.get("TFB200_FB_LANES", "2"))))
+    est = Estimator(cfg, frames_dev, lanes_req)
+    lanes = est.lanes
+    # two pairs of a chunk in flight (handle lanes): pair i on lane i % 2 / its own stream; each lane has its own
+    # post-process scratch.  Chunks stay ordered on the caller's stream.
+    posts = [ops.PostProcess(H, W, forward=forward) for _ in range(lanes)]
+    lane_streams = [torch.cuda.Stream() for _ in range(lanes)] if lanes > 1 else None
+    chunk_state = {"next": None}
+
+    def estimate_chunk(first_pair, n_pairs, outs=None):
+        """n_pairs consecutive pairs: that many solves + post-processes, and one extra prepare when the chunk does
+        not continue the previous one (a rank's chunks of a round are consecutive in frame order: the lanes then run
+        on without a new prepare).  `outs` (raw device addresses, possibly peer memory) receive the post-processed
+        flows."""
+        main = torch.cuda.current_stream()
+        if lane_streams:        # orders the lanes after everything queued on the caller's stream, in particular the
+            for s in lane_streams:      # ring's "slot free" wait of a new round (also when the chunk continues)
+                s.wait_stream(main)
+        if chunk_state["next"] != first_pair:
+            est.begin(first_pair, frame)
+            if io["host"]:
+                feeder.release()
+            if lane_streams:
+                for s in lane_streams:
+                    s.wait_stream(main)
+        flows = []
+        for i in range(n_pairs):
+            lane = est.n % lanes
+            with torch.cuda.stream(lane_streams[lane] if lane_streams else main):
+                flow = est.pair(first_pair + i + 1, None, lane=lane)
+                if io["host"]:
+                    feeder.release()
+                flow.record_stream(main)
+                flows.append(posts[lane](flow, None if outs is None else outs[i]))
+        chunk_state["next"] = first_pair + n_pairs
+        if lane_streams:
+            for s in lane_streams:
+                main.wait_stream(s)
+        return flows
+
+    comp = None
+    mask_png = write_mask_png(mask, f"shard{rank}")
+    video_rgb = frames_dev.flip(-1).contiguous() if any(p is None for p in pixmaps) else None
+    if rank == 0:
+        comp = make_compositor(cfg, mask_png, pixmaps, video_rgb)
+        rgb = [torch.empty((H, W, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        rgb_host = [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        down = torch.cuda.Stream()
+        copied = [None, None]
+        count = {"n": 0}
+    fanout_box = {"f": None, "frames": 0}
+
+    def accumulate(flow):
+        k = count["n"] & 1
+        count["n"] += 1
+        if io["host"] and copied[k] is not None:
+            torch.cuda.current_stream().wait_event(copied[k])   # the D2H out of this buffer is done
+        comp.step(flow, rgb[k])
+        fan = fanout_box["f"]
+        if io["host"] and fan is not None:
+            target = fanout_box["frames"] % world            # frame i leaves through rank i % N's PCIe link
+            fanout_box["frames"] += 1
+            if target != 0:
+                fan.send(rgb[k], target)
+                done = torch.cuda.Event()
+                done.record()
+                copied[k] = done                              # rgb[k] may be rewritten once the peer copy ran
+                return
+        if io["host"]:
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(down):
+                down.wait_event(ready)
+                rgb_host[k].copy_(rgb[k], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(down)
+            copied[k] = ev
+
+    # calibrate F (flow per pair) and A (accumulate per frame) on rank 0, share the plan
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def fresh_chunk(n):
+        chunk_state["next"] = None
+        return estimate_chunk(0, n)
+    fresh_chunk(K)
+    f_ms = timed(lambda: fresh_chunk(K), 2) / K
+    plan = torch.zeros(2, dtype=torch.float64, device="cuda")
+    if rank == 0:
+        fl = fresh_chunk(1)[0]
+        accumulate(fl)
+        a_ms = timed(lambda: accumulate(fl), 4)
+        plan[0], plan[1] = f_ms, a_ms
+        # calibration frames went through the compositor: start the measured stream from a fresh state
+        comp = make_compositor(cfg, mask_png, pixmaps, video_rgb)
+        count["n"] = 0
+    dist.broadcast(plan, src=0)
+    f_ms, a_ms = float(plan[0]), float(plan[1])
+    counts = plan_round(world, Q, f_ms, a_ms)
+    transport = os.environ.get("TFB200_TRANSPORT", "p2p")
+    frames_per_round = sum(counts) * K
+    fan = None
+    if os.environ.get("TFB200_FANOUT", "1") == "1":
+        from transflow_b200.peer import PeerFrameFanout
+        fan = PeerFrameFanout(rank, world, (H, W, 3))
+        fanout_box["f"] = fan
+    e2e_first_round = {"j": None}
+
+    def round_hook(j):
+        # in the end-to-end pass, every non-zero rank queues the D2H of the frames it will be handed
+        if io["host"] and fan is not None and rank != 0:
+            if e2e_first_round["j"] is None:
+                e2e_first_round["j"] = j
+            lo = (j - e2e_first_round["j"]) * frames_per_round
+            fan.expect(sum(1 for i in range(lo, lo + frames_per_round) if i % world == rank))
+    stream = ShardedFlowStream(rank, world, K, counts, estimate_chunk, accumulate, (H, W, 2), "cuda",
+                               transport=transport, round_hook=round_hook)
+    chunk_state["next"] = None
+    # rounds per step so that one step lasts about as long as a single-GPU step
+    rounds_per_step = max(1, int(round(cfg["frames_per_step"] * world / frames_per_round)))
+
+    def timed_rounds(first, warm, steps):
+        stream.run(first, warm)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        stream.run(first + warm, steps)
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t
+
+    n_warm, n_steps = args.warmup * rounds_per_step, args.steps * rounds_per_step
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.timer_enable(True)
+    launches0 = _lib.launch_count()
+    if rank == 0:
+        sampler.mark_begin()
+    ms = timed_rounds(0, n_warm, n_steps)
+    launches_done = _lib.launch_count() - launches0
+    kernel_ms = {tag: _lib.timer_read(tag) for tag in _lib.KERNEL_TAGS}
+    _lib.timer_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the sharded stream must leave rank 0's compositor in the state a single rank reaches on the same frames
+    check = {"frames": (n_warm + n_steps) * frames_per_round}
+    if rank == 0:
+        def state_sum(c):
+            total = 0
+            for layer in c.layers:
+                d = layer.data
+                if d is not None:
+                    total += int(torch.from_numpy(np.ascontiguousarray(d)).long().sum())
+                total += int(torch.from_numpy(np.ascontiguousarray(layer.rgba)).long().sum())
+            return total
+        check["sharded"] = state_sum(comp)
+        replay_frames = min(check["frames"], int(os.environ.get("TFB200_REPLAY_FRAMES", "100000")))
+        if replay_frames == check["frames"]:
+            solo = make_compositor(cfg, mask_png, pixmaps, video_rgb)
+            sharded_comp, comp = comp, solo
+            chunk_state["next"] = None
+            done = 0
+            while done < replay_frames:
+                n = min(K, replay_frames - done)
+                for f in estimate_chunk(done, n):
+                    comp.step(f, rgb[0])
+                done += n
+            torch.cuda.synchronize()
+            check["single_rank_replay"] = state_sum(solo)
+            check["equal"] = check["single_rank_replay"] == check["sharded"]
+            comp = sharded_comp
+            chunk_state["next"] = None
+            if not check["equal"]:
+                raise RuntimeError(f"sharded compositor state differs from the single-rank replay: {check}")
+    dist.barrier()
+
+    # end to end: every frame enters from pinned host memory, every RGB frame returns to it
+    io["host"] = True
+    chunk_state["next"] = None
+    ms_e2e = timed_rounds(n_warm + n_steps, n_warm, n_steps)
+    io["host"] = False
+    launches = torch.tensor([launches_done], dtype=torch.float64, device="cuda")
+    dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        frames = n_steps * stream.frames_per_round
+        fps = frames / (float(ms) / 1000.0)
+        peak, peak_src = measured_peak_gbs()
+        n_px = H * W
+        frame_bytes = algorithmic_bytes_per_frame(cfg, est.engine if cfg["method"] == "farneback" else None)
+        tag, alg_fn, note = ROOFLINE_KERNELS[cfg["method"]]
+        alg = alg_fn(float(n_px), cfg["lk_step"])
+        roofline = None
+        if kernel_ms.get(tag, (0, 0))[1] > 0:
+            tot_ms, n = kernel_ms[tag]
+            achieved = alg / (tot_ms / n / 1000.0) / 1e9
+            traffic, traffic_src = profiled_traffic(tag, (H, W))
+            roofline = {"bound": "hbm", "kernel": tag, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                        "peak_source": peak_src, "avg_launch_ms": tot_ms / n, "launches": n,
+                        "algorithmic_bytes_per_launch": alg,
+                        "timing": "rank 0's launches, CUDA events around each launch on its stream inside the timed "
+                                  "region (two pairs share the SMs there, and the compositor runs beside them)"}
+            if note:
+                roofline["note"] = note
+        ceiling = 1000.0 / a_ms if a_ms > 0 else None
+        line = {
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms) / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(cfg, dict(
+                sharding=f"chunks of {K} pairs; per round {counts} chunks per rank (rank 0 also runs the sequential "
+                         f"accumulate+remap); {rounds_per_step} rounds per step; transport {transport}: "
+                         + ("the producer's last post-process kernel stores the flow into rank 0's ring over NVLink "
+                            "peer memory, counters + cuStreamWaitValue32 order it" if transport == "p2p" else
+                            "batched NCCL send/recv, receives posted one round ahead"),
+                frames_per_step=stream.frames_per_round * rounds_per_step, state_check=check,
+                calibrated_ms={"flow_per_pair": f_ms, "accumulate_per_frame": a_ms},
+                sequential_tail_ceiling_fps=ceiling)),
+            "roofline": roofline,
+            "e2e": {"value": frames / (float(ms_e2e) / 1000.0), "unit": "frames/s",
+                    "h2d_bytes_per_step": int(stream.frames_per_round * rounds_per_step * n_px * 3 * (K + 1) / K),
+                    "d2h_bytes_per_step": int(stream.frames_per_round * rounds_per_step * n_px * 3),
+                    "api": "sharded stream: pinned BGR frames H2D on every rank; RGB frame i leaves through rank i % N's "
+                           "PCIe link (rank 0 hands it over NVLink)" if fan is not None else
+                           "sharded stream: pinned BGR frames H2D on every rank, RGB frames D2H on rank 0"},
+            "gpu_launches": int(launches), "clocks": clocks, "frames_timed": frames,
+            "pipeline_hbm_frac": frame_bytes * fps / 1e9 / (peak * world),
+            "exchange_bytes_per_step": int(sum(counts[1:]) * K * rounds_per_step * n_px * 8),
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+    return 0
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--height", type=int, default=H4K)
-    ap.add_argument("--width", type=int, default=W4K)
+    ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
+    ap.add_argument("--height", type=int, default=0, help="override the config's frame height")
+    ap.add_argument("--width", type=int, default=0, help="override the config's frame width")
+    ap.add_argument("--frames-per-step", type=int, default=0, help="override the config's batch of frames per step")
+    ap.add_argument("--lk-step", type=int, default=1, help="lk_step of the Lucas-Kanade config (1 = dense)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

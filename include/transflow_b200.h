@@ -111,6 +111,10 @@ TF_API int tf_farneback_run(tf_farneback* h, const uint8_t* left, const uint8_t*
                      int variant, void* stream);
 TF_API int tf_farneback_num_levels(const tf_farneback* h);
 TF_API int tf_farneback_level_size(const tf_farneback* h, int level_index, int* width, int* height);
+/* Allocate frame slots [0, slots) and solve lanes [0, lanes) now (at most 3 / 2).  tf_farneback_create allocates two
+ * slots and one lane; a caller that keeps two pairs in flight (tf_farneback_step_lane) reserves 3 / 2 up front so that
+ * no cudaMalloc -- a device-wide synchronisation -- happens inside the frame loop. */
+TF_API int tf_farneback_reserve(tf_farneback* h, int slots, int lanes);
 /* Debug mode: prepare() also writes the finest level's blurred image, which otherwise only exists inside the
  * fused polynomial-expansion kernel (needed by tf_farneback_debug_read(what = 0) on that level). */
 TF_API int tf_farneback_set_debug(tf_farneback* h, int on);

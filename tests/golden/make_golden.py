@@ -363,6 +363,67 @@ def render_cases():
     print("render cases:", len(RENDER_CASES))
 
 
+def lock_cases(tmp):
+    """Reference flow sources whose ``prev_flow`` is read again -- a locked flow (stay / skip mode) and Horn-Schunck's
+    decay -- together with a mask or a convolution kernel: ``post_process`` edits ``prev_flow`` in place only up to
+    the filters there (``numpy.multiply`` / ``numpy.stack`` copy, ``source.py:337-348``), and fully in place without
+    them (quirk Q5).  Also the documented ``math`` / ``random`` / ``numpy`` names inside filter expressions."""
+    import cv2
+    import json
+    from transflow.flow.sources.source import FlowSource
+    from transflow_b200.synthetic import synthetic_clip
+
+    fh, fw, n = 64, 96, 7
+    clip = synthetic_clip(fh, fw, n, seed=5)
+    avi = os.path.join(tmp, "clip_lock.avi")
+    vw = cv2.VideoWriter(avi, cv2.VideoWriter_fourcc(*"FFV1"), 25, (fw, fh))
+    for f in clip:
+        vw.write(f)
+    vw.release()
+    grad = np.clip(np.add.outer(np.linspace(40, 220, fh), np.linspace(0, 35, fw)), 0, 255).astype(np.uint8)
+    p_mask = os.path.join(tmp, "lock_mask.png")
+    save_mask_png(grad, p_mask)
+    p_kernel = os.path.join(tmp, "box3.npy")
+    np.save(p_kernel, np.full((3, 3), 1 / 9))
+    cfgs = {"fb": dict(method="farneback"),
+            "hs": dict(method="horn-schunck", hs_alpha=10.0, hs_iterations=2, hs_decay=0.9, hs_delta=1.0)}
+    for k, c in cfgs.items():
+        with open(os.path.join(tmp, k + ".json"), "w") as fp:
+            json.dump(c, fp)
+    cases = {
+        "stay_mask_fw": dict(cfg="fb", lock_expr="(0.04,0.12),(100,1)", lock_mode="stay", mask_path=p_mask,
+                             flow_filters="scale=1.5", direction="forward"),
+        "stay_kernel_bw": dict(cfg="fb", lock_expr="(0.04,0.12),(100,1)", lock_mode="stay", kernel_path=p_kernel,
+                               direction="backward"),
+        "stay_plain_fw": dict(cfg="fb", lock_expr="(0.04,0.12),(100,1)", lock_mode="stay", flow_filters="scale=0.9",
+                              direction="forward"),
+        "skip_mask_bw": dict(cfg="fb", lock_expr="0.07<t<0.17", lock_mode="skip", mask_path=p_mask,
+                             flow_filters="scale=2", direction="backward"),
+        "hs_decay_mask_fw": dict(cfg="hs", mask_path=p_mask, direction="forward"),
+        "hs_decay_kernel_bw": dict(cfg="hs", kernel_path=p_kernel, flow_filters="scale=1.25", direction="backward"),
+        "usage_math": dict(cfg="fb", flow_filters="scale=1-math.exp(-.5*(t+1));clip=2+math.sin(t)",
+                           direction="backward"),
+        "usage_polar_numpy": dict(cfg="fb", flow_filters="polar=r*(1+numpy.abs(numpy.sin(a))):a+numpy.pi/8*t",
+                                  direction="backward"),
+    }
+    from transflow.utils import load_float_mask
+    out = {"clip": clip, "mask": load_float_mask(p_mask), "kernel/box3": np.load(p_kernel), "framerate": np.array(25.0)}
+    for k, c in cfgs.items():
+        out["config/" + k] = np.array(json.dumps(c))
+    for name, kw in cases.items():
+        kw = dict(kw)
+        cfg = kw.pop("cfg")
+        with FlowSource.from_args(avi, cv_config=os.path.join(tmp, cfg + ".json"), **kw) as src:
+            import itertools
+            flows = np.stack([np.array(f) for f in itertools.islice(src, 9)])   # (the stay tuples extend the length)
+        out[f"{name}/flows"] = flows.astype(np.float32)
+        out[f"{name}/args"] = np.array(json.dumps(dict({k: (os.path.basename(v) if k.endswith("_path") else v)
+                                                         for k, v in kw.items()}, cfg=cfg)))
+        print(name, flows.shape)
+    np.savez_compressed(os.path.join(HERE, "lock_golden.npz"), **out)
+    print("lock cases:", len(cases))
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     if not only or "render" in only:
@@ -377,6 +438,8 @@ if __name__ == "__main__":
             postprocess_cases(tmp)
         if not only or "merge" in only:
             merge_cases(tmp)
+        if not only or "lock" in only:
+            lock_cases(tmp)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

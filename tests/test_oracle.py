@@ -244,3 +244,24 @@ def test_lk_restatement_matches_cv2(case):
     mine = lk_np.dense_flow(g0, g1, 15, 2, step)
     d = np.abs(mine - ref).max(axis=-1)
     assert (d > 0).mean() < 1e-3 and d.max() < 1e-3
+
+
+def test_philox_restatement_matches_random123_known_answers():
+    """Random123's kat_vectors for philox4x32 (7 and 10 rounds): the restatement the device draws are checked with."""
+    from oracle.philox_np import philox4x32, reset_draws
+    kats = [
+        (7, (0, 0, 0, 0), (0, 0), (0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48)),
+        (7, (0xffffffff,) * 4, (0xffffffff,) * 2, (0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662)),
+        (7, (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+         (0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a)),
+        (10, (0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+        (10, (0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ]
+    for rounds, ctr, key, want in kats:
+        got = tuple(int(x) for x in philox4x32(ctr, key, rounds))
+        assert got == want, (rounds, [hex(g) for g in got])
+    u = reset_draws(0x5EED, 3, 33, 47)
+    assert u.shape == (33, 47) and u.dtype == np.float64 and 0.0 <= u.min() and u.max() < 1.0
+    assert abs(u.mean() - 0.5) < 0.03
+    # a pixel pair shares one block; frames and seeds give unrelated fields
+    assert not np.array_equal(u, reset_draws(0x5EED, 4, 33, 47)) and not np.array_equal(u, reset_draws(1, 3, 33, 47))

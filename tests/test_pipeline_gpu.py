@@ -1,0 +1,130 @@
+"""GPU tests of the host-side plugin logic around the kernels: locked flows / Horn-Schunck decay with a mask or a
+kernel (``prev_flow`` aliasing, reference ``source.py:293-363``), the documented filter expressions, and the
+``.ckpt.zip`` write -> resume round trip (reference ``pipeline.py:225-242, 290-303``, ``tests/test_pipeline.py:90-119``)."""
+import itertools
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from tests import golden_util as G  # noqa: E402
+
+LOCK_CASES = ["stay_mask_fw", "stay_kernel_bw", "stay_plain_fw", "skip_mask_bw", "hs_decay_mask_fw",
+              "hs_decay_kernel_bw", "usage_math", "usage_polar_numpy"]
+
+
+def write_avi(path, clip, fps=25):
+    import cv2
+    vw = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"FFV1"), fps, (clip.shape[2], clip.shape[1]))
+    assert vw.isOpened(), "cv2 cannot write FFV1"
+    for f in clip:
+        vw.write(f)
+    vw.release()
+
+
+@pytest.mark.parametrize("name", LOCK_CASES)
+def test_flow_source_lock_and_decay_match_reference(name, tmp_path):
+    """Flows the REAL reference produced (tests/golden/make_golden.py::lock_cases) for sources that read ``prev_flow``
+    again.  A source that post-processed ``prev_flow`` fully in place next to a mask / kernel would re-apply them on
+    every locked frame (the held flow decays) -- far outside these tolerances."""
+    import PIL.Image
+    from transflow_b200.flow import FlowSource
+    from transflow_b200.flow.sources.cv import ArrayCapture
+    z = G.load("lock_golden.npz")
+    args = json.loads(str(z[f"{name}/args"]))
+    cfg_path = tmp_path / "cfg.json"
+    cfg_path.write_text(str(z["config/" + args.pop("cfg")]))
+    if args.get("mask_path"):
+        path = str(tmp_path / "mask.png")
+        PIL.Image.fromarray(np.rint(z["mask"] * 255).astype(np.uint8)).save(path)
+        args["mask_path"] = path
+    if args.get("kernel_path"):
+        path = str(tmp_path / "kernel.npy")
+        np.save(path, z["kernel/box3"])
+        args["kernel_path"] = path
+    want = z[f"{name}/flows"]
+    with FlowSource.from_args(ArrayCapture(z["clip"], 25.0), cv_config=str(cfg_path), **args) as src:
+        flows = list(itertools.islice(src, len(want)))
+    assert len(flows) == len(want)
+    for t, (got, ref) in enumerate(zip(flows, want)):
+        assert got.dtype == np.float32 and got.shape == ref.shape
+        err = np.linalg.norm(got.astype(np.float64) - ref, axis=-1)
+        if args["direction"] == "backward":
+            assert err.mean() <= 0.01 and err.max() <= 0.1, (name, t, err.mean(), err.max())
+        else:       # forward: integer targets; a raw flow 1e-6 off can flip a rounding on a few pixels
+            assert (err > 0).mean() < 1e-2, (name, t, (err > 0).mean())
+
+
+def test_filter_expressions_see_math_random_numpy():
+    """USAGE.md documents ``math`` / ``random`` / ``numpy`` inside expressions (reference utils.py:1-8, :409-414)."""
+    from transflow_b200.utils import parse_lambda_expression
+    assert abs(parse_lambda_expression("1-math.exp(-.5*t)")(2.0) - 0.6321205588285577) < 1e-15
+    assert 0.0 <= parse_lambda_expression("random.random()*t")(1.0) <= 1.0
+    assert parse_lambda_expression("numpy.sqrt(t)")(4.0) == 2.0
+
+
+def _run_pipeline(cfg, **kw):
+    from transflow_b200.pipeline import Pipeline
+    pipe = Pipeline(cfg, **kw)
+    pipe.run()
+    return pipe
+
+
+@pytest.mark.parametrize("layer_kw", [dict(), dict(reset_mode="random", reset_random_factor=0.5)])
+def test_checkpoint_file_round_trip(tmp_path, layer_kw):
+    """The reference's ``test_checkpoint``: run ckpt + 1 frames writing a checkpoint every ckpt frames, resume from
+    the FILE, and the resumed last frame equals the uninterrupted one (diff == 0)."""
+    import PIL.Image
+    from transflow_b200.config import LayerConfig, PixmapSourceConfig
+    from transflow_b200.pipeline import Config
+    from transflow_b200.synthetic import synthetic_clip
+    ckpt, fps = 5, 25
+    h, w = 72, 96
+    clip = synthetic_clip(h, w, ckpt + 3, seed=4)
+    avi = tmp_path / "flow.avi"
+    write_avi(avi, clip, fps)
+    out1 = tmp_path / "1-%d.png"
+    cfg = Config(str(avi), pixmap_sources=[PixmapSourceConfig("cnoise", layers=[0])],
+                 layers=[LayerConfig(0, "moveref", **layer_kw)], output_path=str(out1), direction="forward",
+                 duration_time=(ckpt + 1) / fps, seed=7)
+    pipe = _run_pipeline(cfg, checkpoint_every=ckpt)
+    assert pipe.cursor == ckpt + 1 and pipe.expected_length == ckpt + 1
+    ckpt_path = tmp_path / f"1-%d_{ckpt:05d}.ckpt.zip"
+    assert ckpt_path.is_file(), sorted(p.name for p in tmp_path.iterdir())
+    for i in range(ckpt + 1):
+        assert (tmp_path / f"1-{i}.png").is_file()
+        os.rename(tmp_path / f"1-{i}.png", tmp_path / f"2-{i}.png")
+    pipe2 = _run_pipeline(Config(str(ckpt_path)), checkpoint_every=ckpt)
+    assert pipe2.cursor == ckpt + 1 and pipe2.expected_length == 1
+    assert len(list(tmp_path.glob("1-*.png"))) == 1
+    a = np.asarray(PIL.Image.open(tmp_path / f"1-{ckpt}.png"))
+    b = np.asarray(PIL.Image.open(tmp_path / f"2-{ckpt}.png"))
+    assert a.shape == (h, w, 3) and np.array_equal(a, b)
+    # the archive holds what the reference writes (pipeline.py:227-233)
+    import zipfile
+    with zipfile.ZipFile(ckpt_path) as z:
+        assert sorted(z.namelist()) == ["compositor.bin", "meta.json"]
+        meta = json.loads(z.read("meta.json"))
+    assert meta["cursor"] == ckpt and meta["framerate"] == fps and meta["config"]["flow_path"] == str(avi)
+
+
+def test_layer_masks_and_seed_survive_pickle():
+    """A ``random`` mask is redrawn from its config string on construction; the pickled layer must carry the array
+    (the reference pickles its mask arrays).  Two layers of one compositor draw different reset numbers."""
+    import pickle
+    from transflow_b200.compositor import Compositor
+    from transflow_b200.config import LayerConfig
+    h, w = 24, 40
+    comp = Compositor.from_args(h, w, [LayerConfig(0, "moveref", reset_mode="random", reset_mask="random"),
+                                       LayerConfig(1, "moveref", reset_mode="random")], seed=11)
+    assert comp.layers[0].rng_seed != comp.layers[1].rng_seed
+    other = Compositor.from_args(h, w, [LayerConfig(0, "moveref", reset_mode="random")], seed=12)
+    assert other.layers[0].rng_seed != comp.layers[0].rng_seed
+    clone = pickle.loads(pickle.dumps(comp))
+    np.testing.assert_array_equal(clone.layers[0].reset_mask, comp.layers[0].reset_mask)
+    assert clone.layers[0].rng_seed == comp.layers[0].rng_seed

@@ -1,30 +1,27 @@
 #!/usr/bin/env python
-"""A few steps of the C3 workload at 4K (device-resident), for ncu captures."""
-import os, sys
+"""A few frames of a bench config (default C3 at 4K, device-resident, one pair at a time), for ncu captures."""
+import argparse, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 import bench as B
 from transflow_b200 import ops
-from transflow_b200.compositor import Compositor
-from transflow_b200.compositor.pixmap_source_interface import PixmapSourceInterface, StillQueue
-from transflow_b200.config import LayerConfig
-H, W = int(os.environ.get("PROF_H", 2160)), int(os.environ.get("PROF_W", 3840))
-clip, mask, pixmap = B.build_workload(H, W, 4, seed=0)
+ns = argparse.Namespace(config=os.environ.get("PROF_CONFIG", "C3"), height=int(os.environ.get("PROF_H", 0)),
+                        width=int(os.environ.get("PROF_W", 0)), frames_per_step=0,
+                        lk_step=int(os.environ.get("PROF_LK_STEP", 1)))
+cfg = B.resolve_config(ns)
+H, W = cfg["height"], cfg["width"]
+clip, mask, pixmaps = B.build_workload(cfg, 4)
 frames = torch.from_numpy(clip).cuda()
-fb = ops.Farneback(H, W)
-post = ops.PostProcess(H, W, True)
-comp = Compositor.from_args(H, W, [LayerConfig(0, "moveref", reset_mode="random", reset_random_factor=0.5,
-                                               reset_mask=B.write_mask_png(mask, "prof"))], background_color=B.BG)
-comp.set_sources({0: [PixmapSourceInterface(StillQueue(torch.from_numpy(pixmap).cuda()), np.ones((H, W), bool))]})
+video_rgb = frames.flip(-1).contiguous()
+est = B.Estimator(cfg, frames, 1)
+post = ops.PostProcess(H, W, cfg["direction"] == "forward")
+comp = B.make_compositor(cfg, B.write_mask_png(mask, "prof"), pixmaps, video_rgb)
 rgb = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
-gray = torch.empty((H, W), dtype=torch.uint8, device="cuda")
 flow = torch.empty((H, W, 2), dtype=torch.float32, device="cuda")
-fb.prepare(0, ops.gray_from_bgr(frames[0], gray))
-slot = 0
+est.begin(0)
 for t in range(int(os.environ.get("PROF_STEPS", 3))):
-    cur = slot ^ 1
-    ops.gray_from_bgr(frames[B.frame_order(t + 1, 4)], gray)
-    fb.step(cur, gray, slot, cur, flow); post(flow); comp.step(flow, rgb)
-    slot = cur
+    est.pair(t + 1, flow)
+    post(flow)
+    comp.step(flow, rgb)
 torch.cuda.synchronize()
 print("ok", int(rgb.sum()))

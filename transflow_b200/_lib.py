@@ -82,6 +82,7 @@ SIGNATURES = {
     "tf_farneback_algorithmic_bytes": (_d, [_vp, _i]),
     "tf_farneback_tune": (_i, [_i, _i]),
     "tf_farneback_set_debug": (_i, [_vp, _i]),
+    "tf_farneback_reserve": (_i, [_vp, _i, _i]),
     "tf_floatmap_accumulate": (_i, [_vp, _vp, _vp, _i, _i, C.c_float, C.c_float, _i, _i, _vp]),
     "tf_floatmap_remap": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _u32, _i, _i, _vp]),
     "tf_hs_create": (_i, [C.POINTER(_vp), _i, _i]),

@@ -1049,6 +1049,17 @@ static int ensure_lane(tf_farneback* h, int lane) {
 
 static bool slot_ok(int s) { return s >= 0 && s < FB_SLOTS; }
 
+extern "C" int tf_farneback_reserve(tf_farneback* h, int slots, int lanes) {
+    TF_REQUIRE(h, TF_ERR_INVALID_ARG, "tf_farneback_reserve: null handle");
+    TF_REQUIRE(slots >= 0 && slots <= FB_SLOTS && lanes >= 0 && lanes <= FB_LANES, TF_ERR_INVALID_ARG,
+               "tf_farneback_reserve: at most %d slots and %d lanes", FB_SLOTS, FB_LANES);
+    for (int s = 0; s < slots; s++)
+        if (int e = ensure_slot(h, s)) return e;
+    for (int l = 0; l < lanes; l++)
+        if (int e = ensure_lane(h, l)) return e;
+    return TF_OK;
+}
+
 extern "C" int tf_farneback_prepare(tf_farneback* h, int slot, const uint8_t* gray, void* stream) {
     TF_REQUIRE(h && gray, TF_ERR_INVALID_ARG, "tf_farneback_prepare: null argument");
     TF_REQUIRE(slot_ok(slot), TF_ERR_INVALID_ARG, "tf_farneback_prepare: slot must be in [0, %d)", FB_SLOTS);

@@ -14,9 +14,10 @@
 //    a lower L1 hit rate cost more than the saved loads.)
 //  * phase B: one thread per (column pair, channel): 2m old values into registers, suffix sums, then stream
 //    the new half (64-bit shared accesses); the sums overwrite the old half (dead after this tile);
-//  * phase C: one thread per (row, 8-column segment): the (8 + 2m)-wide window is read with 128-bit shared
-//    loads, horizontal window sums (direct sum + slides), 2x2 solve with error-free fp32 products, 128-bit
-//    stores.
+//  * phase C: one thread per (row, 4-column segment) in the default configuration (SEG = 4: a warp = 8 segments x
+//    4 rows, every warp of the CTA has work; SEG = 8 is the earlier split): the (SEG + 2m)-wide window is read with
+//    128-bit shared loads, horizontal window sums (direct sum + slides), 2x2 solve with error-free fp32 products,
+//    128-bit stores.
 // PITCH = 4 (mod 8) floats: rows are 16-byte aligned and a quarter-warp of phase C (4 segments x 2 rows)
 // touches 8 distinct 16-byte bank groups.
 #pragma once

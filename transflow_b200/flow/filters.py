@@ -62,18 +62,60 @@ class ClipFlowFilter(_ScalarFlowFilter):
     kind = "clip"
 
 
+class _DeviceNumpy:
+    """What ``numpy`` means inside a ``polar`` expression: the reference hands the expressions NumPy arrays
+    ``(r, a)`` (filters.py:79-84) and USAGE.md writes them with ``numpy.sin(a)`` etc.  Here ``r`` and ``a`` are CUDA
+    tensors, so a NumPy function called with a tensor argument runs as the torch function of the same name on the
+    device; anything else is plain NumPy."""
+
+    _ALIASES = {"power": "pow", "absolute": "abs", "arctan2": "atan2", "arcsin": "asin", "arccos": "acos",
+                "arctan": "atan", "mod": "remainder", "concatenate": "cat"}
+
+    def __getattr__(self, name):
+        import numpy
+        target = getattr(numpy, name)
+        if not callable(target) or isinstance(target, type):
+            return target
+        on_device = getattr(torch, self._ALIASES.get(name, name), None)
+
+        def call(*args, **kwargs):
+            ref = next((a for a in args if isinstance(a, torch.Tensor)), None)
+            if ref is None:
+                return target(*args, **kwargs)
+            if on_device is None:
+                raise NotImplementedError(f"numpy.{name} has no device counterpart")
+            args = [a if isinstance(a, torch.Tensor) else torch.as_tensor(a, dtype=ref.dtype, device=ref.device)
+                    for a in args]
+            return on_device(*args, **kwargs)
+        return call
+
+
 class PolarFlowFilter(FlowFilter):
-    """Polar re-parametrisation with user expressions of ``(t, r, a)`` arrays (filters.py:73-87)."""
+    """Polar re-parametrisation with user expressions of ``(t, r, a)`` arrays (filters.py:73-87).  The expressions
+    are arbitrary Python: they run on the device tensors when they are made of operators and ``numpy`` functions
+    torch also has, and on host copies of ``r`` and ``a`` (the reference's own evaluation) when they are not."""
 
     def __init__(self, args):
-        self.expr_radius = parse_lambda_expression(args[0], ("t", "r", "a"))
-        self.expr_theta = parse_lambda_expression(args[1], ("t", "r", "a"))
+        self.exprs = [parse_lambda_expression(a, ("t", "r", "a"), numpy_module=_DeviceNumpy()) for a in args]
+        self.host_exprs = [parse_lambda_expression(a, ("t", "r", "a")) for a in args]
+        self.expr_radius, self.expr_theta = self.exprs
 
     def apply(self, flow, t):
         radius = torch.linalg.vector_norm(flow, dim=2)
         theta = torch.atan2(flow[:, :, 1], flow[:, :, 0])
-        new_radius = self.expr_radius(t, radius, theta)
-        new_theta = self.expr_theta(t, radius, theta)
-        new_theta = new_theta if isinstance(new_theta, torch.Tensor) else torch.full_like(theta, float(new_theta))
+        try:
+            new_radius = self.expr_radius(t, radius, theta)
+            new_theta = self.expr_theta(t, radius, theta)
+        except (NotImplementedError, TypeError, RuntimeError, ValueError, AttributeError):
+            r, a = radius.cpu().numpy(), theta.cpu().numpy()
+            new_radius, new_theta = (e(t, r, a) for e in self.host_exprs)
+
+        def tensor(v):
+            if isinstance(v, torch.Tensor):
+                return v.to(device=flow.device, dtype=torch.float32)
+            import numpy
+            return torch.as_tensor(numpy.broadcast_to(numpy.asarray(v, dtype=numpy.float32), tuple(theta.shape)).copy(),
+                                   device=flow.device)
+        new_radius, new_theta = tensor(new_radius), tensor(new_theta)
         flow[:, :, 1] = new_radius * torch.sin(new_theta)
         flow[:, :, 0] = new_radius * torch.cos(new_theta)

@@ -104,6 +104,14 @@ class ArrayCapture:
         pass
 
 
+class _Uploaded:
+    """A frame on its way into a slot of the device ring."""
+    __slots__ = ("frame", "ready", "slot")
+
+    def __init__(self, frame, ready, slot):
+        self.frame, self.ready, self.slot = frame, ready, slot
+
+
 class CvFlowSource(FlowSource):
 
     @enum.unique
@@ -168,6 +176,7 @@ class CvFlowSource(FlowSource):
         self._engine_key = None
         self._stage = None      # pinned host staging for uploads
         self._copy_stream = None
+        self._dev_ring = None   # device frames the uploads land in
         self._lookahead = None
         #: read one frame ahead so its H2D copy overlaps the current frame's kernels
         self.prefetch = True
@@ -189,11 +198,11 @@ class CvFlowSource(FlowSource):
             raise ValueError("Attribute capture has incorrect type")
 
     # -- frame prep (cv.py:461-466): resize NEAREST on the host if needed, upload, gray on device ------
-    def _upload(self, frame) -> torch.Tensor:
-        """Start the H2D copy of a decoded BGR frame on the side stream; returns the device frame.
-        CUDA tensors pass through, pinned CPU tensors are copied directly, NumPy frames go through
-        a pinned staging buffer."""
-        if isinstance(frame, torch.Tensor) and frame.is_cuda:
+    def _upload(self, frame):
+        """Start the H2D copy of a decoded BGR frame on the side stream into the next slot of a preallocated ring of
+        device frames -> ``_Uploaded``.  CUDA tensors pass through, pinned CPU tensors are copied directly, NumPy
+        frames go through a pinned staging buffer."""
+        if isinstance(frame, _Uploaded) or (isinstance(frame, torch.Tensor) and frame.is_cuda):
             return frame
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream()
@@ -214,22 +223,37 @@ class CvFlowSource(FlowSource):
                 self._stage_events[k].synchronize()     # the previous copy out of this buffer is done
             self._stage[k].numpy()[...] = frame
             src = self._stage[k]
+        # preallocated ring of device frames (no allocation per frame): a slot is overwritten once the
+        # gray conversion that read its previous frame has run
+        if self._dev_ring is None:
+            n = max(2, int(self.pairs_in_flight)) + 2
+            self._dev_ring = [torch.empty((self.height, self.width, 3), dtype=torch.uint8, device="cuda")
+                              for _ in range(n)]
+            self._dev_consumed = [None] * n
+            self._dev_index = 0
+        slot = self._dev_index
+        self._dev_index = (slot + 1) % len(self._dev_ring)
+        dev = self._dev_ring[slot]
         with torch.cuda.stream(self._copy_stream):
-            dev = src.cuda(non_blocking=True)
+            if self._dev_consumed[slot] is not None:
+                self._copy_stream.wait_event(self._dev_consumed[slot])
+            dev.copy_(src, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         if src is not frame and self._stage is not None:
             self._stage_events[self._stage_index] = ev
-        dev._tf_ready = ev
-        return dev
+        return _Uploaded(dev, ev, slot)
 
     def _gray_on_device(self, frame) -> torch.Tensor:
-        bgr = self._upload(frame)
-        ev = getattr(bgr, "_tf_ready", None)
-        if ev is not None:
-            torch.cuda.current_stream().wait_event(ev)
-            bgr.record_stream(torch.cuda.current_stream())
-        return ops.gray_from_bgr(bgr)
+        up = self._upload(frame)
+        if not isinstance(up, _Uploaded):
+            return ops.gray_from_bgr(up)
+        torch.cuda.current_stream().wait_event(up.ready)
+        gray = ops.gray_from_bgr(up.frame)
+        done = torch.cuda.Event()
+        done.record()
+        self._dev_consumed[up.slot] = done
+        return gray
 
     def _read_frame(self):
         """capture.read() with a one-frame look-ahead: the next frame's upload overlaps this
@@ -252,7 +276,8 @@ class CvFlowSource(FlowSource):
             key = ("fb", c.fb_pyr_scale, c.fb_levels, c.fb_winsize, c.fb_iterations, c.fb_poly_n, c.fb_poly_sigma,
                    c.fb_flags)
             make = lambda: ops.Farneback(self.height, self.width, c.fb_pyr_scale, c.fb_levels, c.fb_winsize,  # noqa: E731
-                                         c.fb_iterations, c.fb_poly_n, c.fb_poly_sigma, c.fb_flags)
+                                         c.fb_iterations, c.fb_poly_n, c.fb_poly_sigma, c.fb_flags,
+                                         lanes=max(1, min(2, self.pairs_in_flight)))
         elif m == CvFlowSource.Method.HORN_SCHUNCK:
             key = ("hs",)
             make = lambda: ops.HornSchunck(self.height, self.width)  # noqa: E731

@@ -274,7 +274,9 @@ class FlowSource:
             flow = self.prev_flow
         else:
             flow = self.read_next_flow()
-        self.prev_flow = flow  # aliases the tensor post_process mutates in place (quirk Q5)
+        # prev_flow aliases ``flow``: post_process edits it in place exactly where the reference does (quirk Q5) --
+        # the filters always; the clip / forward scatter only when no mask and no kernel is set
+        self.prev_flow = flow
         if locked and self.lock_mode == FlowSource.LockMode.SKIP:
             self.read_next_flow()
         self.output_frame_index += 1
@@ -286,14 +288,30 @@ class FlowSource:
     def __iter__(self):
         return self
 
+    def _apply_scalar_ops(self, flow, pending):
+        arr, n = ops._pack_flow_ops(pending)
+        ops.check(ops._lib.load().tf_flow_filters(ops.ptr(flow), arr, n, None, ops.ptr(flow), self.height,
+                                                  self.width, ops.stream_ptr()))
+
     def post_process(self, raw):
         """filters -> mask -> kernel -> [forward: clip, round, scatter] -> clip, on the device.
 
         Runs of scalar filters (scale / threshold / clip) are folded into the post-process kernel together with
         the mask multiply; a ``polar`` filter (arbitrary array expressions) splits the run.  With a convolution
         kernel the order of the reference is kept: filters + mask, float64 convolution, then the clip / scatter.
+
+        What happens to ``raw`` follows the reference (source.py:337-363), because ``prev_flow`` aliases it and a
+        locked flow (or Horn-Schunck's decay) reads it again: without mask and kernel every step edits ``raw`` in
+        place; with a mask or a kernel only the filters do (``numpy.multiply`` / ``numpy.stack`` copy there) and the
+        result is a new tensor.
         """
         flow = raw if isinstance(raw, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(raw)).cuda()
+        if self._post is None:
+            mask = None
+            if self.mask is not None:
+                mask = torch.from_numpy(np.ascontiguousarray(self.mask, dtype=np.float32)).cuda()
+            self._post = ops.PostProcess(self.height, self.width, self.direction == FlowSource.Direction.FORWARD,
+                                         mask=mask, kernel=self.kernel)
         pending = []
         t = self.t
         for flt in self.flow_filters:
@@ -301,21 +319,17 @@ class FlowSource:
                 pending.append(flt.op(t))
                 continue
             if pending:
-                arr, n = ops._pack_flow_ops(pending)
-                ops.check(ops._lib.load().tf_flow_filters(ops.ptr(flow), arr, n, None, ops.ptr(flow), self.height,
-                                                          self.width, ops.stream_ptr()))
+                self._apply_scalar_ops(flow, pending)
                 pending = []
             if flt.kind is not None:
                 pending.append(flt.op(t))
             else:
                 flt.apply(flow, t)
-        if self._post is None:
-            mask = None
-            if self.mask is not None:
-                mask = torch.from_numpy(np.ascontiguousarray(self.mask, dtype=np.float32)).cuda()
-            self._post = ops.PostProcess(self.height, self.width, self.direction == FlowSource.Direction.FORWARD,
-                                         mask=mask, kernel=self.kernel)
-        return self._post(flow, ops=pending)
+        if not self._post.copies:
+            return self._post(flow, ops=pending)
+        if pending:
+            self._apply_scalar_ops(flow, pending)      # in place: prev_flow carries the filter edits only
+        return self._post(flow, out=torch.empty_like(flow))
 
     @classmethod
     def from_args(cls, flow_path, use_mvs=False, mask_path=None, kernel_path=None, cv_config=None,

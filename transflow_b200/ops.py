@@ -43,7 +43,7 @@ class Farneback:
     """Device Farneback flow with the parameters of ``CvFlowConfig.fb_*`` (cv.py:275-281)."""
 
     def __init__(self, height, width, pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5,
-                 poly_sigma=1.2, flags=0, r_fp16=None, variant=None, debug=False):
+                 poly_sigma=1.2, flags=0, r_fp16=None, variant=None, debug=False, lanes=1):
         self.lib = _lib.load()
         self.h, self.w = int(height), int(width)
         if variant is None:
@@ -55,6 +55,8 @@ class Farneback:
         check(self.lib.tf_farneback_create(C.byref(self.handle), self.h, self.w, float(pyr_scale), int(levels),
                                            int(winsize), int(iterations), int(poly_n), float(poly_sigma),
                                            int(flags), int(bool(r_fp16))))
+        if lanes > 1:   # two pairs in flight: third frame slot + second solve lane allocated now, not in the frame loop
+            check(self.lib.tf_farneback_reserve(self.handle, 3, int(lanes)))
         if debug:       # keep every pyramid image readable through debug_read
             check(self.lib.tf_farneback_set_debug(self.handle, 1))
 
@@ -223,8 +225,8 @@ class PostProcess:
             self._tmp = torch.empty((self.h, self.w, 2), dtype=torch.float32, device="cuda")
 
     def __call__(self, flow: torch.Tensor, out: torch.Tensor | None = None, ops=None) -> torch.Tensor:
-        """In place by default; ``out`` (same shape, may be peer memory) receives the result instead.
-        ``ops``: [("scale" | "threshold" | "clip", scalar), ...] applied first, in order."""
+        """In place by default; ``out`` (same shape, may be peer memory) receives the result instead and ``flow``
+        keeps its value.  ``ops``: [("scale" | "threshold" | "clip", scalar), ...] applied first, in order."""
         flow = _cuda(flow, torch.float32, "flow")
         if tuple(flow.shape) != (self.h, self.w, 2):
             raise ValueError(f"flow must be ({self.h}, {self.w}, 2), got {tuple(flow.shape)}")
@@ -233,14 +235,21 @@ class PostProcess:
             check(self.lib.tf_flow_filters(ptr(flow), arr, n, ptr(self.mask), ptr(self._tmp), self.h, self.w,
                                            stream_ptr()))
             kh, kw = self.kernel.shape
-            check(self.lib.tf_flow_convolve(ptr(self._tmp), ptr(self.kernel), kh, kw, int(self.forward), ptr(flow),
+            dst = flow if out is None else out
+            check(self.lib.tf_flow_convolve(ptr(self._tmp), ptr(self.kernel), kh, kw, int(self.forward), ptr(dst),
                                             self.h, self.w, stream_ptr()))
-            arr, n, mask = None, 0, None
-        else:
-            mask = self.mask
-        check(self.lib.tf_flow_postprocess_ex(ptr(flow), arr, n, ptr(mask), int(self.forward), ptr(self.owner),
+            check(self.lib.tf_flow_postprocess_ex(ptr(dst), None, 0, None, int(self.forward), ptr(self.owner),
+                                                  None, self.h, self.w, stream_ptr()))
+            return dst
+        check(self.lib.tf_flow_postprocess_ex(ptr(flow), arr, n, ptr(self.mask), int(self.forward), ptr(self.owner),
                                               ptr(out), self.h, self.w, stream_ptr()))
         return flow if out is None else out
+
+    @property
+    def copies(self) -> bool:
+        """True when the reference's ``post_process`` leaves its input alone after the filters (``numpy.multiply``
+        by the mask and ``numpy.stack`` of the convolved channels make copies, source.py:342-348)."""
+        return self.mask is not None or self.kernel is not None
 
 
 MERGE_MODES = {"first": 0, "sum": 1, "average": 2, "difference": 3, "product": 4, "maskbin": 5, "masklin": 6,

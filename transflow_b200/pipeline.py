@@ -9,7 +9,8 @@ CUDA stream so they overlap the kernels of neighbouring frames.
 ``Pipeline(config).run()`` keeps the reference's hot loop (``pipeline.py:545-575``):
 ``flow = next(flow_source)`` -> ``compositor.update(flow)`` -> ``compositor.render()`` ->
 outputs, with ``cursor``, ``Status`` messages, cancel event and ``.ckpt.zip`` checkpoints
-(``pipeline.py:225-242``: ``meta.json`` + pickled compositor).
+(``pipeline.py:225-242``: ``meta.json`` + pickled compositor; a run whose flow path is such an archive
+resumes from it, ``pipeline.py:290-303``).
 """
 import collections
 import io
@@ -79,9 +80,14 @@ class Config:
                     self.layers.append(LayerConfig(li))
                     known.add(li)
 
+    _PLAIN_FIELDS = ("mask_path", "kernel_path", "flow_filters", "seek_time", "duration_time", "repeat", "lock_expr",
+                     "compositor_background", "size", "seed", "extra_flow_paths", "flows_merging_function",
+                     "export_flow", "round_flow", "view_flow", "view_flow_magnitude", "render_scale", "render_colors",
+                     "render_binary")
+
     def todict(self) -> dict:
-        d = {k: getattr(self, k) for k in ("mask_path", "kernel_path", "flow_filters", "seek_time", "duration_time",
-                                           "repeat", "lock_expr", "compositor_background", "size", "seed")}
+        """Same keys as the reference's ``Config.todict`` (config.py:290-323) for the fields kept here."""
+        d = {k: getattr(self, k) for k in self._PLAIN_FIELDS}
         d["flow_path"] = self.flow_path if isinstance(self.flow_path, str) else repr(self.flow_path)
         d["cv_config"] = self.cv_config if isinstance(self.cv_config, (str, type(None))) else self.cv_config.to_dict()
         d["direction"] = FlowSource.Direction.from_arg(self.direction).value
@@ -89,7 +95,39 @@ class Config:
         d["pixmap_sources"] = [p.todict() for p in self.pixmap_sources]
         d["layers"] = [layer.todict() for layer in self.layers]
         d["output_path"] = self.output_path if isinstance(self.output_path, (str, type(None))) else None
+        d["export_flow"] = None if self.export_flow is None else str(self.export_flow)
+        d["size"] = None if self.size is None else list(self.size)
         return d
+
+    @classmethod
+    def fromdict(cls, d: dict):
+        """Inverse of ``todict`` (reference: config.py:258-288); unknown keys of a reference-written dict are ignored."""
+        from .flow.sources.cv import CvFlowConfig
+        cv = d.get("cv_config")
+        if isinstance(cv, dict):
+            cv = CvFlowConfig(**cv)
+        kwargs = {k: d[k] for k in cls._PLAIN_FIELDS if k in d}
+        if kwargs.get("size") is not None:
+            kwargs["size"] = tuple(kwargs["size"])
+        if kwargs.get("extra_flow_paths") is None:
+            kwargs.pop("extra_flow_paths", None)
+        return cls(d["flow_path"], cv_config=cv, direction=d.get("direction", "forward"),
+                   lock_mode=d.get("lock_mode"), output_path=d.get("output_path"),
+                   pixmap_sources=[PixmapSourceConfig.fromdict(x) for x in d.get("pixmap_sources", [])],
+                   layers=[LayerConfig.fromdict(x) for x in d.get("layers", [])], **kwargs)
+
+    def get_secondary_output_path(self, suffix: str) -> str:
+        """``<output or flow path without extension><suffix>`` (config.py:325-341)."""
+        import re
+        base = self.output_path if isinstance(self.output_path, str) else None
+        if base is None:
+            base = self.flow_path if isinstance(self.flow_path, str) else "transflow"
+        path = os.path.splitext(base)[0]
+        if path.endswith(".flow") or path.endswith(".ckpt"):
+            path = path[:-5]
+        if re.match(r".*\.(\d{3})$", path):
+            path = path[:-4]
+        return path + suffix
 
 
 class _IteratorQueue:
@@ -110,7 +148,7 @@ class Pipeline:
     Status = collections.namedtuple("Status", ["cursor", "total", "elapsed", "error"])
 
     def __init__(self, config: Config, status_queue=None, cancel_event=None, checkpoint_every=None,
-                 checkpoint_end=False, checkpoint_path="transflow.ckpt.zip", keep_frames_on_device=False):
+                 checkpoint_end=False, checkpoint_path=None, keep_frames_on_device=False):
         self.config = config
         self.status_queue = status_queue
         self.cancel_event = cancel_event
@@ -132,6 +170,9 @@ class Pipeline:
 
     # -- setup (pipeline.py:290-455) -----------------------------------------------------------------
     def _setup_checkpoint(self):
+        """Resume from a ``.ckpt.zip`` given as the flow path (pipeline.py:290-303): the archive's config replaces
+        ours, shifted by ``cursor / framerate``; the pickled compositor carries the accumulated state."""
+        self._ckpt_meta = {}
         path = self.config.flow_path
         if not (isinstance(path, str) and path.endswith(".ckpt.zip")):
             return
@@ -139,11 +180,12 @@ class Pipeline:
             meta = json.loads(archive.read("meta.json").decode())
             self.compositor = pickle.loads(archive.read("compositor.bin"))
         self._ckpt_meta = meta
-        resumed = meta.get("resume")
-        if resumed is None:
-            raise ValueError("checkpoint was written without resumable flow information")
-        self.config = resumed if isinstance(resumed, Config) else self.config
-        self.cursor = int(meta.get("cursor", 0))
+        self.config = Config.fromdict(meta["config"])
+        shift = meta["cursor"] / meta["framerate"]
+        self.config.seek_time += shift
+        if self.config.duration_time is not None:
+            self.config.duration_time -= shift
+        self.cursor = int(meta["cursor"])
 
     def _setup_flow_source(self):
         c = self.config
@@ -215,7 +257,8 @@ class Pipeline:
         self._scale = (width // fw, height // fh)
         if self.compositor is None:
             self.compositor = Compositor.from_args(height, width, self.config.layers,
-                                                   background_color=self.config.compositor_background)
+                                                   background_color=self.config.compositor_background,
+                                                   seed=self.config.seed)
         interfaces = {}
         for pc, src in zip(self.config.pixmap_sources, opened):
             q = _IteratorQueue(src)
@@ -305,13 +348,18 @@ class Pipeline:
                 layer.sources = src
         meta = {"config": self.config.todict(), "cursor": self.cursor,
                 "framerate": self.flow_source.framerate if self.flow_source else None, "timestamp": time.time()}
-        with zipfile.ZipFile(path or self.checkpoint_path, "w") as archive:
+        if path is None:
+            path = self.checkpoint_path or self.config.get_secondary_output_path(f"_{self.cursor:05d}.ckpt.zip")
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        self.last_checkpoint_path = path
+        with zipfile.ZipFile(path, "w") as archive:
             archive.writestr("meta.json", json.dumps(meta))
             archive.writestr("compositor.bin", blob)
 
     # -- run -----------------------------------------------------------------------------------------
     def run(self):
         start = time.time()
+        self._setup_checkpoint()
         self._setup_flow_source()
         self._setup_pixmaps_and_compositor()
         error = None

@@ -154,9 +154,15 @@ def parse_color(string: str) -> tuple[int, int, int]:
     return ((x >> 16) & 255, (x >> 8) & 255, x & 255)
 
 
-def parse_lambda_expression(expr: str, variables: tuple[str, ...] = ("t",)) -> Callable:
-    """``"1 + t"`` -> ``lambda t: 1 + t`` (trusted CLI input, as in the reference)."""
-    return eval("lambda " + ",".join(variables) + ": " + expr)  # noqa: S307
+def parse_lambda_expression(expr: str, variables: tuple[str, ...] = ("t",), numpy_module=None) -> Callable:
+    """``"1 + t"`` -> ``lambda t: 1 + t`` (trusted CLI input, as in the reference).  The expression sees what the
+    reference's ``utils`` module offers it (utils.py:1-8, USAGE.md: ``math``, ``random``, ``numpy``, ...)."""
+    import math
+    import os
+    import random
+    npm = np if numpy_module is None else numpy_module      # polar filters pass a tensor-aware stand-in
+    scope = {"math": math, "random": random, "numpy": npm, "np": npm, "os": os, "re": re}
+    return eval("lambda " + ",".join(variables) + ": " + expr, scope)  # noqa: S307
 
 
 def parse_timestamp(value) -> float | None:
