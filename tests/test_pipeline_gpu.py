@@ -128,3 +128,37 @@ def test_layer_masks_and_seed_survive_pickle():
     clone = pickle.loads(pickle.dumps(comp))
     np.testing.assert_array_equal(clone.layers[0].reset_mask, comp.layers[0].reset_mask)
     assert clone.layers[0].rng_seed == comp.layers[0].rng_seed
+
+
+def test_level_a_reference_pipeline_runs_with_swapped_classes(tmp_path):
+    """INTEGRATION.md level A: the reference's own multi-process ``Pipeline`` (flow SourceProcess -> queue ->
+    main loop -> output process, reference pipeline.py:56-136, 440-455, 545-575) drives this package's
+    ``FlowSource`` / ``Compositor`` / ``PixmapSourceInterface`` in place of its own, and writes the frames the
+    stock run writes (backward direction: integer state bit-exact given flows within 1e-5 px of cv2)."""
+    import subprocess
+    import sys
+    import PIL.Image
+    from transflow_b200.synthetic import synthetic_clip
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isfile(os.path.join(root, "baseline", "_ref", "transflow", "pipeline.py")):
+        pytest.skip("baseline/_ref (the installed reference) is not present")
+    h, w, n = 96, 128, 6
+    avi = tmp_path / "flow.avi"
+    write_avi(avi, synthetic_clip(h, w, n, seed=9))
+    outs = {}
+    for mode in ("stock", "swapped"):
+        out = tmp_path / mode
+        env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+        if mode == "stock":
+            env["CUDA_VISIBLE_DEVICES"] = ""        # the stock run is the reference's CPU path, nothing else
+        res = subprocess.run([sys.executable, os.path.join(root, "tests", "level_a_runner.py"), mode, str(avi), str(out)],
+                             capture_output=True, text=True, timeout=600, env=env)
+        assert res.returncode == 0 and f"cursor {n - 1}" in res.stdout, (mode, res.stdout[-2000:], res.stderr[-4000:])
+        if mode == "swapped":
+            assert "transflow_b200.compositor" in res.stdout, res.stdout
+        frames = sorted(out.glob("*.png"), key=lambda p: int(p.stem))
+        assert len(frames) == n - 1, (mode, [p.name for p in frames])
+        outs[mode] = [np.asarray(PIL.Image.open(p)) for p in frames]
+    for t, (a, b) in enumerate(zip(outs["stock"], outs["swapped"])):
+        assert a.shape == (h, w, 3)
+        np.testing.assert_array_equal(a, b, err_msg=f"frame {t}")

@@ -19,7 +19,7 @@ lib = _lib.load()
 BASE = int(os.environ.get("SWEEP_BASE", "8"))
 VARIANTS = [int(v) for v in os.environ.get("SWEEP_VARIANTS", "18,19,20").split(",")]
 ROWS = [int(v) for v in os.environ.get("SWEEP_ROWS", "0,84,112,140,168,224,252,280").split(",")]
-KEY = {v: 3 for v in (18, 19, 20)}
+KEY = {v: 3 for v in (18, 19, 20, 21, 22)}   # others: key 0 (half-buffer kernel rows)
 try:
     for (h, w) in ((540, 960), (1080, 1920)):
         clip = synthetic_clip(h, w, 2, seed=2)

@@ -77,7 +77,8 @@ class Compositor:
         global NumPy generator instead (pipeline.py), which the ``reset_rng = "numpy"`` parity mode still follows."""
         layers = [Layer.from_args(config, height, width, []) for config in layer_configs]
         for layer in layers:
-            layer.set_seed(seed)
+            if hasattr(layer, "set_seed"):
+                layer.set_seed(seed)
         return cls(height, width, layers, background_color=background_color)
 
     def set_sources(self, pixmap_interfaces: dict[int, list[PixmapSourceInterface]]):

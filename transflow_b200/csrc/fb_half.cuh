@@ -166,6 +166,45 @@ __device__ __forceinline__ void fbh_phase_b(float* __restrict__ old_half, const 
     }
 }
 
+// phase B of fb_half.cuh with PAIRS column pairs per channel (PAIRS >= COLS / 2, 2 * PAIRS <= PITCH): the padding
+// pairs are summed too (finite or not, phase C never reads them) so that consecutive items stay on consecutive banks
+// across a channel boundary
+template <typename G, int NT, int PAIRS>
+__device__ __forceinline__ void fbr_phase_b(float* __restrict__ old_half, const float* __restrict__ new_half, int tid) {
+    for (int item = tid; item < 5 * PAIRS; item += NT) {
+        int c = item / PAIRS, lx = 2 * (item - c * PAIRS);
+        float2* oc = reinterpret_cast<float2*>(old_half + c * G::CHS + lx);
+        const float2* nc = reinterpret_cast<const float2*>(new_half + c * G::CHS + lx);
+        float2 v[G::TY];
+#pragma unroll
+        for (int j = 0; j < G::TY; j++) v[j] = oc[j * (G::PITCH / 2)];
+#pragma unroll
+        for (int j = G::TY - 2; j >= 0; j--) {
+            v[j].x += v[j + 1].x;
+            v[j].y += v[j + 1].y;
+        }
+        float2 p = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < G::TY; j++) {
+            float2 nv = nc[j * (G::PITCH / 2)];
+            p = j == 0 ? nv : make_float2(p.x + nv.x, p.y + nv.y);
+            oc[j * (G::PITCH / 2)] = make_float2(v[j].x + p.x, v[j].y + p.y);
+        }
+    }
+}
+
+// smallest number of column pairs >= base with 2 * pairs == chs (mod 32) that still fits the pitch; else base
+constexpr int fbr_pick_pairs(int base, int pitch, int chs) {
+    for (int p = base; 2 * p <= pitch; p++)
+        if ((2 * p - chs) % 32 == 0) return p;
+    return base;
+}
+template <int MR, int TX>
+struct FbrPairs {
+    using G = FbhGeom<MR, TX, true>;
+    static constexpr int PAIRS = fbr_pick_pairs((G::COLS + 1) / 2, G::PITCH, G::CHS);
+};
+
 // ---- phase C: horizontal window sums + 2x2 solve + store for the tile's nout rows ----
 template <typename G, int TX, int NT, bool VEC, int SEG = 8>
 __device__ __forceinline__ void fbh_phase_c(const float* __restrict__ old_half, float2* __restrict__ flow_out, int tid,
@@ -316,7 +355,7 @@ struct FbhCfg {
     static constexpr int CTAS = FIT < 1 ? 1 : (FIT > WANT ? WANT : FIT);
 };
 
-template <int MR, int TX, int NT, int WANT, bool VEC, int SEG = 8>
+template <int MR, int TX, int NT, int WANT, bool VEC, int SEG = 8, bool BFIX = false>
 __global__ void __launch_bounds__(NT, (FbhCfg<MR, TX, NT, WANT, VEC>::CTAS))
     k_fb_iter_half(const float4* __restrict__ R0q, const float* __restrict__ R0e, const float4* __restrict__ R1q,
                    const float* __restrict__ R1e, const float2* __restrict__ flow_in, float2* __restrict__ flow_out,
@@ -382,7 +421,8 @@ __global__ void __launch_bounds__(NT, (FbhCfg<MR, TX, NT, WANT, VEC>::CTAS))
         const int ty = y0 + (hh - 1) * G::TY;
         const int nout = min(G::TY, y1 - ty);
         __syncthreads();
-        fbh_phase_b<G, NT, VEC>(old_half, new_half, tid);
+        if constexpr (BFIX) fbr_phase_b<G, NT, FbrPairs<MR, TX>::PAIRS>(old_half, new_half, tid);
+        else fbh_phase_b<G, NT, VEC>(old_half, new_half, tid);
         __syncthreads();
         fbh_phase_c<G, TX, NT, VEC, SEG>(old_half, flow_out, tid, x0, ty, nout, w, h, reg, clip);
         __syncthreads();  // the next tile's phase A overwrites the half phase C just read
@@ -393,11 +433,11 @@ __global__ void __launch_bounds__(NT, (FbhCfg<MR, TX, NT, WANT, VEC>::CTAS))
 extern int g_fbh_rows;
 extern int g_fbh_rows_min_px;  // the rows override applies to levels of at least this many pixels (key 2)
 
-template <int MR, int TX, int NT, int WANT, bool VEC, int SEG = 8>
+template <int MR, int TX, int NT, int WANT, bool VEC, int SEG = 8, bool BFIX = false>
 static int fb_launch_half(const float* R0, const float* R1, const float2* in, float2* dst, int w, int h, double scale,
                           int clip, cudaStream_t st) {
     using G = FbhGeom<MR, TX, VEC>;
-    auto kern = k_fb_iter_half<MR, TX, NT, WANT, VEC, SEG>;
+    auto kern = k_fb_iter_half<MR, TX, NT, WANT, VEC, SEG, BFIX>;
     static int resident = 0;
     if (!resident) {
         TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
@@ -456,6 +496,8 @@ static int fb_iterate_half(tf_farneback* h, FbLevel& L, const RT* R0, const RT* 
         e = variant == 5   ? fb_launch_half<MR, 128, 512, 2, true>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)  \
             : variant == 6 ? fb_launch_half<MR, 64, 256, 4, true>(R0f, R1f, in, dst, L.w, L.h, scale, c, st) \
             : variant == 17 ? fb_launch_half<MR, 64, 256, 4, true, 4>(R0f, R1f, in, dst, L.w, L.h, scale, c, st) \
+            : variant == 23 ? fb_launch_half<MR, 128, 512, 2, true, 4, true>(R0f, R1f, in, dst, L.w, L.h, scale, c, st) \
+            : variant == 24 ? fb_launch_half<MR, 64, 256, 4, true, 4, true>(R0f, R1f, in, dst, L.w, L.h, scale, c, st) \
             : variant == 7 ? fb_launch_half<MR, 64, 256, 3, false>(R0f, R1f, in, dst, L.w, L.h, scale, c, st) \
                            : fb_launch_half<MR, 64, 256, 4, false>(R0f, R1f, in, dst, L.w, L.h, scale, c, st); \
         break;

@@ -49,45 +49,6 @@ struct FbrMaps {
     CUtensorMap r1q, r1e;
 };
 
-// phase B of fb_half.cuh with PAIRS column pairs per channel (PAIRS >= COLS / 2, 2 * PAIRS <= PITCH): the padding
-// pairs are summed too (finite or not, phase C never reads them) so that consecutive items stay on consecutive banks
-// across a channel boundary
-template <typename G, int NT, int PAIRS>
-__device__ __forceinline__ void fbr_phase_b(float* __restrict__ old_half, const float* __restrict__ new_half, int tid) {
-    for (int item = tid; item < 5 * PAIRS; item += NT) {
-        int c = item / PAIRS, lx = 2 * (item - c * PAIRS);
-        float2* oc = reinterpret_cast<float2*>(old_half + c * G::CHS + lx);
-        const float2* nc = reinterpret_cast<const float2*>(new_half + c * G::CHS + lx);
-        float2 v[G::TY];
-#pragma unroll
-        for (int j = 0; j < G::TY; j++) v[j] = oc[j * (G::PITCH / 2)];
-#pragma unroll
-        for (int j = G::TY - 2; j >= 0; j--) {
-            v[j].x += v[j + 1].x;
-            v[j].y += v[j + 1].y;
-        }
-        float2 p = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int j = 0; j < G::TY; j++) {
-            float2 nv = nc[j * (G::PITCH / 2)];
-            p = j == 0 ? nv : make_float2(p.x + nv.x, p.y + nv.y);
-            oc[j * (G::PITCH / 2)] = make_float2(v[j].x + p.x, v[j].y + p.y);
-        }
-    }
-}
-
-// smallest number of column pairs >= base with 2 * pairs == chs (mod 32) that still fits the pitch; else base
-constexpr int fbr_pick_pairs(int base, int pitch, int chs) {
-    for (int p = base; 2 * p <= pitch; p++)
-        if ((2 * p - chs) % 32 == 0) return p;
-    return base;
-}
-template <int MR, int TX>
-struct FbrPairs {
-    using G = FbhGeom<MR, TX, true>;
-    static constexpr int PAIRS = fbr_pick_pairs((G::COLS + 1) / 2, G::PITCH, G::CHS);
-};
-
 template <int MR, int TX, int NT>
 __global__ void __launch_bounds__(NT, 2)
     k_fb_iter_ring(const __grid_constant__ FbrMaps maps, const float4* __restrict__ R0q, const float* __restrict__ R0e,
@@ -239,6 +200,214 @@ __global__ void __launch_bounds__(NT, 2)
     }
 }
 
+// ---- ring kernel, ROW PAIRS (variants 21 / 22) -------------------------------------------------------------------
+// Phase A with one thread per (halo'd column, PAIR of consecutive matrix rows): when the two pixels sample the same
+// columns one row apart -- the common case, the flow is smooth -- the lower tap row of the first pixel is the upper
+// tap row of the second, so a pair costs 3 tap rows (6 x 128-bit + 6 x 32-bit shared loads) instead of 4, and its
+// address arithmetic, bounds tests and loop overhead are paid once.  The R0 / flow operands of the NEXT pair are
+// requested before the current pair's taps (two rows of look-ahead), and those of a half's first pair before phases B
+// and C of the previous half, so that no global load is waited for inside phase A.  7 row pairs per half.
+struct FbrOps {
+    float2 f;
+    float4 q;
+    float e;
+};
+__device__ __forceinline__ FbrOps fbr_load_ops(const float4* __restrict__ R0q, const float* __restrict__ R0e,
+                                               const float2* __restrict__ flow_in, unsigned at) {
+    FbrOps o;
+    o.f = flow_in ? fbh_ld_stream(flow_in + at) : make_float2(0.f, 0.f);
+    o.q = fbh_ld_stream(R0q + at);
+    o.e = fbh_ld_stream(R0e + at);
+    return o;
+}
+
+template <int MR, int TX, int NT>
+__global__ void __launch_bounds__(NT, 2)
+    k_fb_iter_ring2(const __grid_constant__ FbrMaps maps, const float4* __restrict__ R0q, const float* __restrict__ R0e,
+                    const float4* __restrict__ R1q, const float* __restrict__ R1e, const float2* __restrict__ flow_in,
+                    float2* __restrict__ flow_out, int w, int h, float reg, int rows_per_cta, int clip) {
+    using G = FbhGeom<MR, TX, true>;
+    using B = FbrGeom<MR, TX>;
+    constexpr int NG = NT / G::COLS;
+    constexpr int NP = G::TY / 2;  // row pairs per half
+    static_assert(NT >= G::COLS, "one thread per halo'd column needed");
+    extern __shared__ __align__(128) float smem_f[];
+    char* base = reinterpret_cast<char*>(smem_f);
+    const float4* boxq = reinterpret_cast<const float4*>(base);
+    const float* boxe = reinterpret_cast<const float*>(base + B::QBYTES);
+    float* ring = reinterpret_cast<float*>(base + B::QBYTES + B::EBYTES);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + B::QBYTES + B::EBYTES + G::SMEM);
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TX;
+    const int y0 = blockIdx.y * rows_per_cta;
+    const int y1 = min(h, y0 + rows_per_cta);
+    const int ntiles = (y1 - y0 + G::TY - 1) / G::TY;
+    const int nsb = 2 * ntiles + 3;
+    const unsigned uw = (unsigned)w;
+
+    int ox = 0, oy = 0;
+    if (flow_in) {
+        const int cy = clampi((y0 + y1) >> 1, 0, h - 1), cx = clampi(x0 + TX / 2, 0, w - 1);
+        const float2 fc = __ldg(flow_in + (unsigned)cy * uw + (unsigned)cx);
+        ox = __float2int_rd(fminf(fmaxf(fc.x, -4096.f), 4096.f));
+        oy = __float2int_rd(fminf(fmaxf(fc.y, -4096.f), 4096.f));
+    }
+    const int bx0 = x0 - MR - B::GL + ox;
+    const int ex0 = bx0 & ~3;
+    const int ry0 = y0 - MR - B::GU + oy;
+
+    auto issue = [&](int sb) {
+        const int s = sb % B::NSLOT;
+        const uint32_t bar = fbh_smem_u32(bars + s);
+        fbs_mbar_expect_tx(bar, B::TX_BYTES);
+        fbm_tensor_g2s(fbh_smem_u32(boxq + s * B::SB * B::BW), &maps.r1q, 2 * bx0, ry0 + B::SB * sb, bar);
+        fbm_tensor_g2s(fbh_smem_u32(boxe + s * B::SB * B::BE), &maps.r1e, ex0, ry0 + B::SB * sb, bar);
+    };
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.r1q)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.r1e)) : "memory");
+        for (int s = 0; s < B::NSLOT; s++) fbs_mbar_init(fbh_smem_u32(bars + s), 1);
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int sb = 0; sb < B::NSLOT && sb < nsb; sb++) issue(sb);
+
+    const int lxA = tid % G::COLS, rg = tid / G::COLS;
+    const bool activeA = rg < NG;
+    const int gxA = clampi(x0 - MR + lxA, 0, w - 1);
+    const float fgx = (float)gxA;
+
+    // operands of the pair (rows 2 pr, 2 pr + 1) of the half whose first matrix row is gyb
+    auto row_at = [&](int gyb, int r) { return (unsigned)clampi(gyb + r, 0, h - 1) * uw + (unsigned)gxA; };
+    FbrOps na, nb;  // the NEXT pair's operands (in flight)
+    na.f = nb.f = make_float2(0.f, 0.f);
+    na.q = nb.q = make_float4(0.f, 0.f, 0.f, 0.f);
+    na.e = nb.e = 0.f;
+    if (activeA) {
+        na = fbr_load_ops(R0q, R0e, flow_in, row_at(y0 - MR, 2 * rg));
+        nb = fbr_load_ops(R0q, R0e, flow_in, row_at(y0 - MR, 2 * rg + 1));
+    }
+
+    for (int hh = 0; hh <= ntiles; hh++) {
+        float* new_half = ring + (hh & 1) * G::HALF;
+        const int gy_base = y0 - MR + hh * G::TY;
+        for (int sb = hh == 0 ? 0 : 2 * hh + 1; sb <= 2 * hh + 2; sb++)
+            if (!fbm_mbar_wait(fbh_smem_u32(bars + sb % B::NSLOT), (uint32_t)((sb / B::NSLOT) & 1))) return;
+        if (activeA) {
+            const int byh = ry0 + G::TY * hh;
+            const int rbase = B::SB * ((2 * hh) % B::NSLOT);
+#pragma unroll 1
+            for (int pr = rg; pr < NP; pr += NG) {
+                const FbrOps oa = na, ob = nb;
+                const int gya = clampi(gy_base + 2 * pr, 0, h - 1), gyb = clampi(gy_base + 2 * pr + 1, 0, h - 1);
+                // next pair: this half's, or the first pair of the next half (it then waits through phases B and C)
+                {
+                    const bool more = pr + NG < NP;
+                    const int nbase = more ? gy_base : gy_base + G::TY;
+                    const int npr = more ? pr + NG : rg;
+                    if (more || hh < ntiles) {
+                        na = fbr_load_ops(R0q, R0e, flow_in, row_at(nbase, 2 * npr));
+                        nb = fbr_load_ops(R0q, R0e, flow_in, row_at(nbase, 2 * npr + 1));
+                    }
+                }
+                const int x1a = __float2int_rd(fgx + oa.f.x), y1a = __float2int_rd((float)gya + oa.f.y);
+                const int x1b = __float2int_rd(fgx + ob.f.x), y1b = __float2int_rd((float)gyb + ob.f.y);
+                const bool ina = (unsigned)x1a < (unsigned)(w - 1) && (unsigned)y1a < (unsigned)(h - 1);
+                const bool inb = (unsigned)x1b < (unsigned)(w - 1) && (unsigned)y1b < (unsigned)(h - 1);
+                const int bxa = x1a - bx0, bya = y1a - byh, bxb = x1b - bx0, byb = y1b - byh;
+                const bool sta = (unsigned)bxa < (unsigned)(B::BW - 1) && (unsigned)bya < (unsigned)(B::RES - 1);
+                const bool stb = (unsigned)bxb < (unsigned)(B::BW - 1) && (unsigned)byb < (unsigned)(B::RES - 1);
+                const float aa[5] = {oa.q.x, oa.q.y, oa.q.z, oa.q.w, oa.e};
+                const float ab[5] = {ob.q.x, ob.q.y, ob.q.z, ob.q.w, ob.e};
+                float* dst = new_half + (2 * pr) * G::PITCH + lxA;
+                float mm[5];
+                auto ring_row = [&](int by) {
+                    int r = by + rbase;
+                    return r - (r >= B::RR ? B::RR : 0);
+                };
+                auto next_row = [&](int r) { return r + 1 == B::RR ? 0 : r + 1; };
+                auto ld = [&](int r, int bx, int x1) {
+                    FbhTaps t;
+                    const float4* q = boxq + r * B::BW + bx;
+                    const float* e = boxe + r * B::BE + (x1 - ex0);
+                    t.q0 = q[0]; t.q1 = q[1]; t.e0 = e[0]; t.e1 = e[1];
+                    return t;
+                };
+                if (__ballot_sync(__activemask(), (ina && !sta) || (inb && !stb)) == 0) {
+                    // shared-memory taps only
+                    FbhTaps top, bot;
+                    const int r0a = ring_row(bya), r1a = next_row(r0a);
+                    if (ina) {
+                        top = ld(r0a, bxa, x1a);
+                        bot = ld(r1a, bxa, x1a);
+                    }
+                    fbh_matrix(aa, oa.f, gxA, gya, w, h, ina, top, bot, mm);
+#pragma unroll
+                    for (int c = 0; c < 5; c++) dst[c * G::CHS] = mm[c];
+                    if (inb) {
+                        if (ina && x1b == x1a && y1b == y1a + 1) {
+                            top = bot;                         // the row below the first pixel's: already here
+                            bot = ld(next_row(r1a), bxb, x1b);
+                        } else {
+                            const int r0b = ring_row(byb);
+                            top = ld(r0b, bxb, x1b);
+                            bot = ld(next_row(r0b), bxb, x1b);
+                        }
+                    }
+                    fbh_matrix(ab, ob.f, gxA, gyb, w, h, inb, top, bot, mm);
+#pragma unroll
+                    for (int c = 0; c < 5; c++) dst[G::PITCH + c * G::CHS] = mm[c];
+                } else {
+                    // a tap of this warp lies outside the resident ring: per-pixel choice, global gather where needed
+                    FbhTaps top, bot;
+                    if (ina) {
+                        if (sta) {
+                            const int r0a = ring_row(bya);
+                            top = ld(r0a, bxa, x1a);
+                            bot = ld(next_row(r0a), bxa, x1a);
+                        } else {
+                            const unsigned q = (unsigned)y1a * uw + (unsigned)x1a;
+                            top = fbh_load_taps(R1q, R1e, q);
+                            bot = fbh_load_taps(R1q, R1e, q + uw);
+                        }
+                    }
+                    fbh_matrix(aa, oa.f, gxA, gya, w, h, ina, top, bot, mm);
+#pragma unroll
+                    for (int c = 0; c < 5; c++) dst[c * G::CHS] = mm[c];
+                    if (inb) {
+                        if (stb) {
+                            const int r0b = ring_row(byb);
+                            top = ld(r0b, bxb, x1b);
+                            bot = ld(next_row(r0b), bxb, x1b);
+                        } else {
+                            const unsigned q = (unsigned)y1b * uw + (unsigned)x1b;
+                            top = fbh_load_taps(R1q, R1e, q);
+                            bot = fbh_load_taps(R1q, R1e, q + uw);
+                        }
+                    }
+                    fbh_matrix(ab, ob.f, gxA, gyb, w, h, inb, top, bot, mm);
+#pragma unroll
+                    for (int c = 0; c < 5; c++) dst[G::PITCH + c * G::CHS] = mm[c];
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            fbs_fence_proxy_async();
+            if (2 * hh + 5 < nsb) issue(2 * hh + 5);
+            if (2 * hh + 6 < nsb) issue(2 * hh + 6);
+        }
+        if (hh == 0) continue;
+        float* old_half = ring + ((hh & 1) ^ 1) * G::HALF;
+        const int ty = y0 + (hh - 1) * G::TY;
+        const int nout = min(G::TY, y1 - ty);
+        fbr_phase_b<G, NT, FbrPairs<MR, TX>::PAIRS>(old_half, new_half, tid);
+        __syncthreads();
+        fbh_phase_c<G, TX, NT, true, 4>(old_half, flow_out, tid, x0, ty, nout, w, h, reg, clip);
+        __syncthreads();
+    }
+}
+
 // ---- host side ----
 static int fbr_map2d(CUtensorMap* m, const void* basep, CUtensorMapDataType dtype, uint32_t elem_bytes, uint64_t inner,
                      uint64_t rows, uint32_t box_inner, uint32_t box_rows) {
@@ -262,12 +431,15 @@ static int fbr_map2d(CUtensorMap* m, const void* basep, CUtensorMapDataType dtyp
 
 extern int g_fbr_rows;  // rows per CTA of the ring kernel (0 = heuristic), tf_farneback_tune key 3
 
-template <int MR, int TX, int NT>
+template <int MR, int TX, int NT, bool PAIRS = false>
 static int fb_launch_ring(const float* R0, const float* R1, const float2* in, float2* dst, int w, int h, double scale,
                           int clip, cudaStream_t st) {
     using G = FbhGeom<MR, TX, true>;
     using B = FbrGeom<MR, TX>;
-    auto kern = k_fb_iter_ring<MR, TX, NT>;
+    void (*kern)(const FbrMaps, const float4*, const float*, const float4*, const float*, const float2*, float2*, int, int,
+                 float, int, int);
+    if constexpr (PAIRS) kern = k_fb_iter_ring2<MR, TX, NT>;
+    else kern = k_fb_iter_ring<MR, TX, NT>;
     static int resident = 0;
     if (!resident) {
         TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::SMEM));
@@ -301,7 +473,8 @@ static int fb_launch_ring(const float* R0, const float* R1, const float2* in, fl
     return TF_OK;
 }
 
-// variants 18 / 19 / 20: 256 / 320 / 384 threads per CTA (3 / 4 / 4 phase-A row groups), 2 CTAs per SM
+// variants 18 / 19 / 20: 256 / 320 / 384 threads per CTA (3 / 4 / 4 phase-A row groups), 2 CTAs per SM;
+// `threads` < 0: the row-pair kernel (variants 21 / 22: 256 / 320 threads)
 template <typename RT>
 static int fb_iterate_ring(tf_farneback* h, FbLevel& L, const RT* R0, const RT* R1, float2* final_buf, float2* other_buf,
                            bool zero_init, int clip, bool finest, cudaStream_t st, int threads) {
@@ -322,6 +495,8 @@ static int fb_iterate_ring(tf_farneback* h, FbLevel& L, const RT* R0, const RT* 
             ScopedKernelTimer timer(finest ? TFK_FB_ITER_FINEST : -1, st);
             e = threads == 384   ? fb_launch_ring<7, 64, 384>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)
                 : threads == 320 ? fb_launch_ring<7, 64, 320>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)
+                : threads == -256 ? fb_launch_ring<7, 64, 256, true>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)
+                : threads == -320 ? fb_launch_ring<7, 64, 320, true>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)
                                  : fb_launch_ring<7, 64, 256>(R0f, R1f, in, dst, L.w, L.h, scale, c, st);
         }
         if (e) return e;

@@ -38,6 +38,8 @@ class FlowSource:
                 return cls.FORWARD
             if isinstance(arg, cls):
                 return arg
+            if isinstance(arg, enum.Enum):      # the reference's own Direction enum (same member names)
+                return cls[arg.name]
             if isinstance(arg, int):
                 return cls(arg)
             table = {"forward": cls.FORWARD, "backward": cls.BACKWARD}
@@ -56,6 +58,8 @@ class FlowSource:
                 return cls.STAY
             if isinstance(arg, cls):
                 return arg
+            if isinstance(arg, enum.Enum):      # the reference's own LockMode enum
+                return cls[arg.name]
             if isinstance(arg, int):
                 return cls(arg)
             table = {"stay": cls.STAY, "skip": cls.SKIP}

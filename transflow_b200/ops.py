@@ -12,10 +12,10 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 
 
-#: solve kernel variant used when none is requested: 8 = half-buffer kernel (configuration 17) on the large pyramid
-#: levels, rolling-tile kernel on the small ones; 3 rolling tile everywhere; 4-7, 17 half-buffer configurations; 9-16
-#: staged experiments; 0 / 2 fused streaming
-#: (float / double sums in shared memory); 1 unfused reference kernels
+#: solve kernel variant used when none is requested: 8 = half-buffer kernel (configuration 24) on the large pyramid
+#: levels, rolling-tile kernel on the small ones; 3 rolling tile everywhere; 4-7, 17, 23, 24 half-buffer configurations;
+#: 9-16 staged experiments; 18-22 ring kernels (R1 taps from a TMA-staged rolling row ring in shared memory); 0 / 2 fused
+#: streaming (float / double sums in shared memory); 1 unfused reference kernels
 DEFAULT_FB_VARIANT = 8
 
 
