@@ -839,11 +839,25 @@ class HostFrameFeeder:
         self.used[self._last] = ev
 
 
+class _QueuedChunk(list):
+    """Flows of a chunk queued with join=False: ready() orders the current stream after that chunk only."""
+
+    def __init__(self, flows):
+        super().__init__(flows)
+        self.events = []
+
+    def ready(self):
+        import torch
+        cur = torch.cuda.current_stream()
+        for ev in self.events:
+            cur.wait_event(ev)
+
+
 def run_sharded(args, cfg, rank, world, local):
     import torch
     import torch.distributed as dist
     from transflow_b200 import _lib, ops
-    from transflow_b200.distributed import ShardedFlowStream, plan_round
+    from transflow_b200.distributed import ShardedFlowStream, plan_rank0_pairs, plan_round
 
     H, W = cfg["height"], cfg["width"]
     K, Q = 8, 4
@@ -863,24 +877,43 @@ def run_sharded(args, cfg, rank, world, local):
     # post-process scratch.  Chunks stay ordered on the caller's stream.
     posts = [ops.PostProcess(H, W, forward=forward) for _ in range(lanes)]
     lane_streams = [torch.cuda.Stream() for _ in range(lanes)] if lanes > 1 else None
+    est_main = torch.cuda.Stream()
     chunk_state = {"next": None}
 
-    def estimate_chunk(first_pair, n_pairs, outs=None):
+    def join_lanes():
+        if lane_streams:
+            main = torch.cuda.current_stream()
+            for s in lane_streams:
+                main.wait_stream(s)
+
+    def estimate_chunk(first_pair, n_pairs, outs=None, gate=None, join=True):
         """n_pairs consecutive pairs: that many solves + post-processes, and one extra prepare when the chunk does
-        not continue the previous one (a rank's chunks of a round are consecutive in frame order: the lanes then run
-        on without a new prepare).  `outs` (raw device addresses, possibly peer memory) receive the post-processed
-        flows."""
+        not continue the previous one (a rank's chunks are consecutive in frame order within a round: the lanes then
+        run on without a new prepare and WITHOUT draining -- the lanes are never ordered after the caller's stream
+        between chunks).  `outs` (raw device addresses, possibly peer memory) receive the post-processed flows;
+        `gate` is queued on every stream that stores into them (the ring's "slot free" wait of a new round);
+        join=False leaves the caller's stream unordered after the chunk (the caller joins before it reads)."""
         main = torch.cuda.current_stream()
-        if lane_streams:        # orders the lanes after everything queued on the caller's stream, in particular the
-            for s in lane_streams:      # ring's "slot free" wait of a new round (also when the chunk continues)
-                s.wait_stream(main)
-        if chunk_state["next"] != first_pair:
-            est.begin(first_pair, frame)
-            if io["host"]:
-                feeder.release()
+        if gate is not None:
+            gate()
             if lane_streams:
                 for s in lane_streams:
-                    s.wait_stream(main)
+                    with torch.cuda.stream(s):
+                        gate()
+        if chunk_state["next"] != first_pair:
+            # the first frame's gray image + expansion are built on the estimator's own stream, ordered after the
+            # lanes (they may still read the slot) but NOT after the caller's stream: on rank 0 that stream holds the
+            # accumulation of a whole round
+            with torch.cuda.stream(est_main if lane_streams else main):
+                if lane_streams:
+                    for s in lane_streams:
+                        est_main.wait_stream(s)
+                est.begin(first_pair, frame)
+                if io["host"]:
+                    feeder.release()
+            if lane_streams:
+                for s in lane_streams:
+                    s.wait_stream(est_main)
         flows = []
         for i in range(n_pairs):
             lane = est.n % lanes
@@ -891,10 +924,15 @@ def run_sharded(args, cfg, rank, world, local):
                 flow.record_stream(main)
                 flows.append(posts[lane](flow, None if outs is None else outs[i]))
         chunk_state["next"] = first_pair + n_pairs
-        if lane_streams:
-            for s in lane_streams:
-                main.wait_stream(s)
-        return flows
+        if join:
+            join_lanes()
+            return flows
+        done = _QueuedChunk(flows)
+        for s in (lane_streams or [main]):
+            ev = torch.cuda.Event()
+            ev.record(s)
+            done.events.append(ev)
+        return done
 
     comp = None
     mask_png = write_mask_png(mask, f"shard{rank}")
@@ -962,8 +1000,10 @@ def run_sharded(args, cfg, rank, world, local):
     dist.broadcast(plan, src=0)
     f_ms, a_ms = float(plan[0]), float(plan[1])
     counts = plan_round(world, Q, f_ms, a_ms)
+    # rank 0's share counted in pairs and queued beside its accumulation (TFB200_RANK0_PAIRS=chunks: whole chunks first)
+    p0 = plan_rank0_pairs(world, Q, K, f_ms, a_ms) if os.environ.get("TFB200_RANK0_PAIRS", "pairs") == "pairs" else None
     transport = os.environ.get("TFB200_TRANSPORT", "p2p")
-    frames_per_round = sum(counts) * K
+    frames_per_round = sum(counts) * K if p0 is None else sum(counts[1:]) * K + p0
     fan = None
     if os.environ.get("TFB200_FANOUT", "1") == "1":
         from transflow_b200.peer import PeerFrameFanout
@@ -979,7 +1019,7 @@ def run_sharded(args, cfg, rank, world, local):
             lo = (j - e2e_first_round["j"]) * frames_per_round
             fan.expect(sum(1 for i in range(lo, lo + frames_per_round) if i % world == rank))
     stream = ShardedFlowStream(rank, world, K, counts, estimate_chunk, accumulate, (H, W, 2), "cuda",
-                               transport=transport, round_hook=round_hook)
+                               transport=transport, round_hook=round_hook, rank0_pairs=p0, join=join_lanes)
     chunk_state["next"] = None
     # rounds per step so that one step lasts about as long as a single-GPU step
     rounds_per_step = max(1, int(round(cfg["frames_per_step"] * world / frames_per_round)))
@@ -1079,8 +1119,11 @@ def run_sharded(args, cfg, rank, world, local):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms) / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(cfg, dict(
-                sharding=f"chunks of {K} pairs; per round {counts} chunks per rank (rank 0 also runs the sequential "
-                         f"accumulate+remap); {rounds_per_step} rounds per step; transport {transport}: "
+                sharding=(f"chunks of {K} pairs; per round {counts} chunks per rank" if p0 is None else
+                          f"chunks of {K} pairs; per round {counts[1:]} chunks per producer rank and {p0} pairs on rank 0, "
+                          "queued beside its accumulation") +
+                         f" (rank 0 also runs the sequential accumulate+remap); {rounds_per_step} rounds per step; "
+                         f"transport {transport}: "
                          + ("the producer's last post-process kernel stores the flow into rank 0's ring over NVLink "
                             "peer memory, counters + cuStreamWaitValue32 order it" if transport == "p2p" else
                             "batched NCCL send/recv, receives posted one round ahead"),
@@ -1097,6 +1140,10 @@ def run_sharded(args, cfg, rank, world, local):
             "gpu_launches": int(launches), "clocks": clocks, "frames_timed": frames,
             "pipeline_hbm_frac": frame_bytes * fps / 1e9 / (peak * world),
             "exchange_bytes_per_step": int(sum(counts[1:]) * K * rounds_per_step * n_px * 8),
+            "scaling_ceiling": {"producers": world - 1, "flow_ms_per_pair": f_ms, "accumulate_ms_per_frame": a_ms,
+                                "fps_if_producers_never_wait": (world - 1) * 1000.0 / f_ms
+                                + ((p0 or 0) / (Q * K)) * 1000.0 / f_ms,
+                                "sequential_tail_fps": ceiling},
         }
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()

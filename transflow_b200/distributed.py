@@ -36,6 +36,18 @@ def plan_round(world: int, q: int, flow_ms: float, accumulate_ms: float) -> list
     return [c0] + [q] * (world - 1)
 
 
+def plan_rank0_pairs(world: int, q: int, k: int, flow_ms: float, accumulate_ms: float) -> int:
+    """Pairs rank 0 estimates itself per round when its share is counted in PAIRS, not whole chunks: with every
+    producer owning ``q * k`` pairs, rank 0 (which also accumulates all ``p0 + (world - 1) * q * k`` frames) finishes
+    with the producers for ``p0 = q k (F - (world - 1) A) / (F + A)``, rounded down, in ``[0, q k]``.  At 8 ranks the
+    whole-chunk plan leaves rank 0 without any estimation work although a quarter of its time is free."""
+    if world == 1:
+        return q * k
+    f, a = max(flow_ms, 1e-9), max(accumulate_ms, 0.0)
+    p0 = q * k * (f - (world - 1) * a) / (f + a)
+    return int(max(0, min(q * k, np.floor(p0 + 1e-9))))
+
+
 def round_slots(counts: list) -> list:
     """Owner rank of every chunk slot of a round, in stream order (rank 0's chunks first)."""
     owners = []
@@ -51,37 +63,59 @@ class ShardedFlowStream:
     ``accumulate(flow)`` consumes flows strictly in frame order (rank 0 only).
     Works with any ``torch.distributed`` backend: tensors only need to live on the device the
     backend moves (CUDA for nccl, CPU for gloo).
+
+    A round is a list of chunk slots ``(owner, pairs)`` in stream order.  By default rank 0's ``counts[0]`` chunks
+    come first, then every producer's; with ``rank0_pairs`` given, rank 0 instead owns ONE chunk of that many pairs
+    at the END of the round, and its estimation is queued ONE ROUND AHEAD (``estimate_chunk(..., join=False)`` on the
+    estimator's own streams; the returned list may carry a ``ready()`` method that orders the caller's stream after
+    that chunk only): like a producer, rank 0's estimator then runs a round ahead of the accumulation, which never
+    waits for it.
     """
 
     def __init__(self, rank, world, chunk_pairs, counts, estimate_chunk, accumulate, flow_shape, device,
-                 group=None, transport="nccl", round_hook=None):
+                 group=None, transport="nccl", round_hook=None, rank0_pairs=None, join=None):
         self.rank, self.world, self.k = rank, world, chunk_pairs
         self.transport = transport
         self.round_hook = round_hook      # called on every rank with the round index before the round starts
         self.counts = list(counts)
-        self.owners = round_slots(self.counts)
-        self.cpr = len(self.owners)
+        self.rank0_pairs = rank0_pairs
+        self.join = join                  # (unused: chunks queued with join=False carry their own ready())
+        if rank0_pairs is None:
+            self.slots = [(owner, chunk_pairs) for owner in round_slots(self.counts)]
+        else:
+            self.slots = [(owner, chunk_pairs) for owner in round_slots([0] + self.counts[1:])]
+            if rank0_pairs > 0:
+                self.slots.append((0, int(rank0_pairs)))
+        self.owners = [owner for owner, _ in self.slots]
+        self.offsets = [0]
+        for _, n in self.slots:
+            self.offsets.append(self.offsets[-1] + n)
+        self.cpr = len(self.slots)
         self.estimate_chunk, self.accumulate = estimate_chunk, accumulate
         self.flow_shape, self.device, self.group = tuple(flow_shape), device, group
         self.frames_accumulated = 0
-        self._recv = {}      # (round parity, slot) -> K receive buffers
+        self._ahead = {}     # round -> {slot: flows} of rank 0's own chunks queued ahead (rank0_pairs mode)
+        self._recv = {}      # (round parity, slot) -> receive buffers
         self.ring = None
         if transport == "p2p" and world > 1:
             from .peer import PeerFlowRing
-            flows_per_round = [c * chunk_pairs for c in self.counts]
+            flows_per_round = [sum(n for owner, n in self.slots if owner == r) for r in range(world)]
             self.ring = PeerFlowRing(rank, world, flows_per_round, self.flow_shape, group)
             self._published = 0                       # producer: flows published so far
             self._expected = [0] * world              # rank 0: flows consumed so far per producer
 
     @property
     def frames_per_round(self) -> int:
-        return self.cpr * self.k
+        return self.offsets[-1]
+
+    def _first_pair(self, round_index: int, slot: int) -> int:
+        return round_index * self.frames_per_round + self.offsets[slot]
 
     def _recv_buffers(self, parity: int, slot: int):
         key = (parity, slot)
         if key not in self._recv:
             self._recv[key] = [torch.empty(self.flow_shape, dtype=torch.float32, device=self.device)
-                               for _ in range(self.k)]
+                               for _ in range(self.slots[slot][1])]
         return self._recv[key]
 
     def _post_receives(self, round_index: int) -> dict:
@@ -94,37 +128,62 @@ class ShardedFlowStream:
                 pending[slot] = dist.batch_isend_irecv(ops)
         return pending
 
+    def _own_chunks_ahead(self, round_index: int, last_round: int) -> dict:
+        """rank0_pairs mode: make sure rank 0's own chunks of this round AND the next one (inside the run) are queued,
+        without ordering the caller's stream after them; returns this round's."""
+        if self.rank0_pairs is None:
+            return {}
+        for jj in (round_index, round_index + 1):
+            if jj <= last_round and jj not in self._ahead:
+                self._ahead[jj] = {slot: self.estimate_chunk(self._first_pair(jj, slot), n, join=False)
+                                   for slot, (owner, n) in enumerate(self.slots) if owner == 0}
+        return self._ahead.pop(round_index)
+
+    @staticmethod
+    def _own_flows(flows):
+        if hasattr(flows, "ready"):
+            flows.ready()         # the caller's stream waits for that chunk (not for chunks queued after it)
+        return flows
+
     def _run_p2p(self, first_round: int, n_rounds: int):
         """Same schedule; flows land in rank 0's ring by peer stores, counters replace send/recv."""
         ring = self.ring
+        last_round = first_round + n_rounds - 1
         for j in range(first_round, first_round + n_rounds):
-            base_chunk = j * self.cpr
             if self.round_hook is not None:
                 self.round_hook(j)
             if self.rank == 0:
+                ahead = self._own_chunks_ahead(j, last_round)
                 index = [0] * self.world              # next ring slot per producer in this round
-                for slot, owner in enumerate(self.owners):
+                total = [sum(n for o, n in self.slots if o == r) for r in range(self.world)]
+                for slot, (owner, n) in enumerate(self.slots):
                     if owner == 0:
-                        flows = self.estimate_chunk((base_chunk + slot) * self.k, self.k)
+                        if slot in ahead:
+                            flows = self._own_flows(ahead[slot])
+                        else:
+                            flows = self.estimate_chunk(self._first_pair(j, slot), n)
                     else:
-                        self._expected[owner] += self.k
+                        self._expected[owner] += n
                         ring.wait_ready(owner, self._expected[owner])
-                        flows = [ring.slot_tensor(owner, j, index[owner] + i) for i in range(self.k)]
-                        index[owner] += self.k
+                        flows = [ring.slot_tensor(owner, j, index[owner] + i) for i in range(n)]
+                        index[owner] += n
                     for f in flows:
                         self.accumulate(f)
                         self.frames_accumulated += 1
-                    if owner != 0 and index[owner] == self.counts[owner] * self.k:
+                    if owner != 0 and index[owner] == total[owner]:
                         ring.release(owner, j)        # every flow of this producer's round is consumed
             else:
-                ring.wait_slot_free(j)
                 i = 0
-                for slot, owner in enumerate(self.owners):
+                first = True
+                for slot, (owner, n) in enumerate(self.slots):
                     if owner == self.rank:
-                        outs = [ring.slot_address(j, i + n) for n in range(self.k)]
-                        self.estimate_chunk((base_chunk + slot) * self.k, self.k, outs)
-                        i += self.k
-                        self._published += self.k
+                        outs = [ring.slot_address(j, i + m) for m in range(n)]
+                        # the ring's "slot free" wait of a new round goes on every stream the estimator stores from
+                        gate = (lambda jj=j: ring.wait_slot_free(jj)) if first else None
+                        self.estimate_chunk(self._first_pair(j, slot), n, outs, gate)
+                        first = False
+                        i += n
+                        self._published += n
                         ring.publish(self._published)
 
     def run(self, first_round: int, n_rounds: int):
@@ -140,10 +199,13 @@ class ShardedFlowStream:
                 if self.round_hook is not None:
                     self.round_hook(j)
                 upcoming = self._post_receives(j + 1) if j < last else {}
-                base_chunk = j * self.cpr
-                for slot, owner in enumerate(self.owners):
+                ahead = self._own_chunks_ahead(j, last)
+                for slot, (owner, n) in enumerate(self.slots):
                     if owner == 0:
-                        flows = self.estimate_chunk((base_chunk + slot) * self.k, self.k)
+                        if slot in ahead:
+                            flows = self._own_flows(ahead[slot])
+                        else:
+                            flows = self.estimate_chunk(self._first_pair(j, slot), n)
                     else:
                         for w in pending[slot]:
                             w.wait()
@@ -157,11 +219,10 @@ class ShardedFlowStream:
             for j in range(first_round, last + 1):
                 if self.round_hook is not None:
                     self.round_hook(j)
-                base_chunk = j * self.cpr
                 works, keep = [], []
-                for slot, owner in enumerate(self.owners):
+                for slot, (owner, n) in enumerate(self.slots):
                     if owner == self.rank:
-                        flows = [f.contiguous() for f in self.estimate_chunk((base_chunk + slot) * self.k, self.k)]
+                        flows = [f.contiguous() for f in self.estimate_chunk(self._first_pair(j, slot), n)]
                         keep.append(flows)              # alive until the sends have completed
                         ops = [dist.P2POp(dist.isend, f, 0, self.group) for f in flows]
                         works += dist.batch_isend_irecv(ops)
