@@ -24,7 +24,8 @@ struct LkLevel {
 
 struct tf_lucas_kanade {
     int H, W, win, max_level, step;
-    int variant;  // 0 = warp-per-point tracker (default), 1 = thread-per-point reference kernel
+    int variant;  // 0 = warp-per-point, column mapping (default for win <= 16); 2 = warp-per-point, linear mapping;
+                  // 1 = thread-per-point reference kernel
     int gw, gh;  // grid of tracked points
     std::vector<LkLevel> lv;
     float2* next_pts;
@@ -342,6 +343,213 @@ __global__ void __launch_bounds__(256, 4) k_lk_track_warp(const uint8_t* __restr
     }
 }
 
+// ---- warp-per-point tracker, column mapping (default for windows up to 16 x 16) -------------------------------
+// Same algorithm and the same exact integer sums as k_lk_track_warp, reorganised around what bounds the tracker
+// (instruction issue and L1 tag lookups):
+//   * lane = (window column, upper / lower half of the rows): lanes 0..WIN-1 own rows 0..R0-1 of their column, lanes
+//     16..16+WIN-1 rows R0..WIN-1.  A load instruction then reads ONE image row per half-warp (15 consecutive bytes:
+//     2 cache lines per instruction instead of one line per window row), and a lane walks down its column: the
+//     bottom taps of a window pixel are the top taps of the next one, so a pixel costs 2 loads instead of 4 (18 per
+//     lane and iteration instead of 32);
+//   * the per-lane partial sums fit 32 bits (<= 8 products of 13 x 12 bits), so the inner loop is 32-bit IMADs and the
+//     warp total is formed by four REDUX instructions (low / high 16 bits separately, recombined exactly in 64 bits)
+//     instead of two 64-bit shuffle trees.
+// The value of every sum is identical to k_lk_track_warp's, so the tracks are bit-identical to that kernel.
+__device__ __forceinline__ long long lk_redux_exact(int v) {
+    const int lo = __reduce_add_sync(0xffffffffu, v & 0xffff);
+    const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
+    return (long long)hi * 65536ll + (long long)lo;
+}
+
+template <int WIN, bool SHFL>
+__global__ void __launch_bounds__(256, 4) k_lk_track_cols(const uint8_t* __restrict__ I, const uint8_t* __restrict__ J,
+                                                         const short2* __restrict__ D, float2* __restrict__ next_pts,
+                                                         int w, int h, int gw, int gh, int step, int level, int is_top) {
+    static_assert(WIN >= 3 && WIN <= 16, "one half-warp per window row group");
+    constexpr int R0 = (WIN + 1) / 2;  // rows of the upper half
+    const int lane = threadIdx.x & 31;
+    const int col = lane & 15, half = lane >> 4;
+    const bool active = col < WIN;
+    const int r0 = half ? R0 : 0;             // first window row of this lane
+    const int nr = half ? WIN - R0 : R0;      // its number of rows
+    const long long pid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (pid >= (long long)gw * gh) return;
+    const int gy = (int)(pid / gw), gx = (int)(pid - (long long)gy * gw);
+    const float lscale = 1.f / (float)(1 << level);
+    const float halfw = (float)(WIN - 1) * 0.5f;
+    float px = (float)(gx * step) * lscale, py = (float)(gy * step) * lscale;
+    float2 np;
+    if (is_top) {
+        np = make_float2(px, py);
+    } else {
+        np = next_pts[pid];
+        np.x *= 2.f;
+        np.y *= 2.f;
+    }
+    if (lane == 0) next_pts[pid] = np;  // stored before any test (points that fail keep this value)
+    px -= halfw;
+    py -= halfw;
+    const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+    if (ipx < -WIN || ipx >= w || ipy < -WIN || ipy >= h) return;
+    const LkWeights q = lk_weights(px - (float)ipx, py - (float)ipy);
+    const bool insideI = ipx >= 0 && ipy >= 0 && ipx + WIN < w && ipy + WIN < h;
+    const float FLT_SCALE = 1.f / (float)(1 << 20);
+    const bool unit = (q.w01 | q.w10 | q.w11) == 0;  // then w00 == 1 << LK_W_BITS: the template is the raw tap
+
+    // template of this lane's column segment + covariance of the interpolated derivatives
+    int ival[R0], dxv[R0], dyv[R0];
+    int a11 = 0, a12 = 0, a22 = 0;
+#pragma unroll
+    for (int k = 0; k < R0; k++) ival[k] = dxv[k] = dyv[k] = 0;
+    if (active) {
+        if (insideI) {
+            const size_t at0 = (size_t)(ipy + r0) * w + ipx + col;
+            if (unit) {
+#pragma unroll
+                for (int k = 0; k < R0; k++) {
+                    if (k < nr) {
+                        const size_t at = at0 + (size_t)k * w;
+                        ival[k] = (int)__ldg(I + at) << 5;
+                        const short2 d = __ldg(D + at);
+                        dxv[k] = d.x;
+                        dyv[k] = d.y;
+                    }
+                }
+            } else {
+                int ia[R0 + 1], ib[R0 + 1];
+                short2 da[R0 + 1], db[R0 + 1];
+#pragma unroll
+                for (int k = 0; k <= R0; k++) {
+                    ia[k] = ib[k] = 0;
+                    da[k] = db[k] = make_short2(0, 0);
+                    if (k <= nr) {
+                        const size_t at = at0 + (size_t)k * w;
+                        ia[k] = __ldg(I + at); ib[k] = __ldg(I + at + 1);
+                        da[k] = __ldg(D + at); db[k] = __ldg(D + at + 1);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < R0; k++) {
+                    if (k < nr) {
+                        ival[k] = lk_descale(ia[k] * q.w00 + ib[k] * q.w01 + ia[k + 1] * q.w10 + ib[k + 1] * q.w11, LK_W_BITS - 5);
+                        dxv[k] = lk_descale(da[k].x * q.w00 + db[k].x * q.w01 + da[k + 1].x * q.w10 + db[k + 1].x * q.w11, LK_W_BITS);
+                        dyv[k] = lk_descale(da[k].y * q.w00 + db[k].y * q.w01 + da[k + 1].y * q.w10 + db[k + 1].y * q.w11, LK_W_BITS);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < R0; k++) {
+                if (k < nr) {
+                    const int X = ipx + col, Y = ipy + r0 + k;
+                    int i00 = lk_img(I, X, Y, w, h, false), i01 = lk_img(I, X + 1, Y, w, h, false);
+                    int i10 = lk_img(I, X, Y + 1, w, h, false), i11 = lk_img(I, X + 1, Y + 1, w, h, false);
+                    short2 d00 = lk_der(D, X, Y, w, h, false), d01 = lk_der(D, X + 1, Y, w, h, false);
+                    short2 d10 = lk_der(D, X, Y + 1, w, h, false), d11 = lk_der(D, X + 1, Y + 1, w, h, false);
+                    ival[k] = lk_descale(i00 * q.w00 + i01 * q.w01 + i10 * q.w10 + i11 * q.w11, LK_W_BITS - 5);
+                    dxv[k] = lk_descale(d00.x * q.w00 + d01.x * q.w01 + d10.x * q.w10 + d11.x * q.w11, LK_W_BITS);
+                    dyv[k] = lk_descale(d00.y * q.w00 + d01.y * q.w01 + d10.y * q.w10 + d11.y * q.w11, LK_W_BITS);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R0; k++) {  // rows beyond nr hold zeros
+            a11 += dxv[k] * dxv[k];
+            a12 += dxv[k] * dyv[k];
+            a22 += dyv[k] * dyv[k];
+        }
+    }
+    float A11 = (float)lk_redux_exact(a11) * FLT_SCALE, A12 = (float)lk_redux_exact(a12) * FLT_SCALE,
+          A22 = (float)lk_redux_exact(a22) * FLT_SCALE;
+    float Dd = A11 * A22 - A12 * A12;
+    float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * WIN * WIN);
+    if (minEig < 1e-4f || Dd < 1.1920929e-07f) return;
+    Dd = 1.f / Dd;
+
+    float nx = np.x - halfw, ny = np.y - halfw;
+    float pdx = 0.f, pdy = 0.f;
+    for (int j = 0; j < 30; j++) {
+        int inx = (int)floorf(nx), iny = (int)floorf(ny);
+        if (inx < -WIN || inx >= w || iny < -WIN || iny >= h) break;
+        const LkWeights r = lk_weights(nx - (float)inx, ny - (float)iny);
+        const bool insideJ = inx >= 0 && iny >= 0 && inx + WIN < w && iny + WIN < h;
+        int b1 = 0, b2 = 0;
+        if (SHFL && WIN < 16 && insideJ) {
+            // every lane of a half-warp loads its column's taps (lane 15: the column right of the window); the right
+            // taps come from the neighbouring lane by shuffle instead of a second load
+            const uint8_t* p = J + ((size_t)(iny + r0) * w + inx + col);
+            int ja[R0 + 1], jb[R0 + 1];
+#pragma unroll
+            for (int k = 0; k <= R0; k++) {
+                ja[k] = 0;
+                if (k <= nr) ja[k] = __ldg(p + (size_t)k * w);
+            }
+#pragma unroll
+            for (int k = 0; k <= R0; k++) jb[k] = __shfl_down_sync(0xffffffffu, ja[k], 1);
+            if (active) {
+#pragma unroll
+                for (int k = 0; k < R0; k++) {
+                    if (k < nr) {
+                        const int diff = lk_descale(ja[k] * r.w00 + jb[k] * r.w01 + ja[k + 1] * r.w10 + jb[k + 1] * r.w11,
+                                                    LK_W_BITS - 5) - ival[k];
+                        b1 += diff * dxv[k];
+                        b2 += diff * dyv[k];
+                    }
+                }
+            }
+        } else if (active) {
+            if (insideJ) {
+                const uint8_t* p = J + ((size_t)(iny + r0) * w + inx + col);
+                int ja[R0 + 1], jb[R0 + 1];
+#pragma unroll
+                for (int k = 0; k <= R0; k++) {
+                    ja[k] = jb[k] = 0;
+                    if (k <= nr) {
+                        ja[k] = __ldg(p + (size_t)k * w);
+                        jb[k] = __ldg(p + (size_t)k * w + 1);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < R0; k++) {
+                    if (k < nr) {
+                        const int diff = lk_descale(ja[k] * r.w00 + jb[k] * r.w01 + ja[k + 1] * r.w10 + jb[k + 1] * r.w11,
+                                                    LK_W_BITS - 5) - ival[k];
+                        b1 += diff * dxv[k];
+                        b2 += diff * dyv[k];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < R0; k++) {
+                    if (k < nr) {
+                        const int X = inx + col, Y = iny + r0 + k;
+                        const int j00 = lk_img(J, X, Y, w, h, false), j01 = lk_img(J, X + 1, Y, w, h, false);
+                        const int j10 = lk_img(J, X, Y + 1, w, h, false), j11 = lk_img(J, X + 1, Y + 1, w, h, false);
+                        const int diff = lk_descale(j00 * r.w00 + j01 * r.w01 + j10 * r.w10 + j11 * r.w11, LK_W_BITS - 5) - ival[k];
+                        b1 += diff * dxv[k];
+                        b2 += diff * dyv[k];
+                    }
+                }
+            }
+        }
+        float fb1 = (float)lk_redux_exact(b1) * FLT_SCALE, fb2 = (float)lk_redux_exact(b2) * FLT_SCALE;
+        float dx = (A12 * fb2 - A22 * fb1) * Dd, dy = (A12 * fb1 - A11 * fb2) * Dd;
+        nx += dx;
+        ny += dy;
+        float2 o = make_float2(nx + halfw, ny + halfw);
+        bool stop = (double)dx * dx + (double)dy * dy <= 1e-4;  // epsilon^2, epsilon = 0.01
+        if (!stop && j > 0 && fabsf(dx + pdx) < 0.01f && fabsf(dy + pdy) < 0.01f) {
+            o.x -= dx * 0.5f;
+            o.y -= dy * 0.5f;
+            stop = true;
+        }
+        if (lane == 0) next_pts[pid] = o;
+        if (stop) break;
+        pdx = dx;
+        pdy = dy;
+    }
+}
+
 // flow = p1 - p0, block-replicated (numpy.kron) back to (H, W), optional final clip
 __global__ void __launch_bounds__(256) k_lk_flow_out(const float2* __restrict__ next_pts, float2* __restrict__ flow,
                                                      int H, int W, int gw, int step, int clip) {
@@ -444,7 +652,16 @@ extern "C" int tf_lk_run(tf_lucas_kanade* h, const uint8_t* left, const uint8_t*
 #define TF_LKW(K)                                                                                                  \
     k_lk_track_warp<K><<<wgrid, 256, 0, st>>>(L.img[0], L.img[1], L.deriv, h->next_pts, L.w, L.h, h->gw, h->gh, h->step, \
                                               h->win, l, l == top)
-            if (h->variant == 1 || kmax > 31)   // thread-per-point reference kernel (and very large windows)
+            if (h->variant == 0 && h->win == 15)
+                k_lk_track_cols<15, true><<<wgrid, 256, 0, st>>>(L.img[0], L.img[1], L.deriv, h->next_pts, L.w, L.h, h->gw, h->gh,
+                                                                 h->step, l, l == top);
+            else if (h->variant == 3 && h->win == 15)
+                k_lk_track_cols<15, false><<<wgrid, 256, 0, st>>>(L.img[0], L.img[1], L.deriv, h->next_pts, L.w, L.h, h->gw, h->gh,
+                                                                  h->step, l, l == top);
+            else if (h->variant == 0 && h->win == 9)
+                k_lk_track_cols<9, true><<<wgrid, 256, 0, st>>>(L.img[0], L.img[1], L.deriv, h->next_pts, L.w, L.h, h->gw, h->gh,
+                                                                h->step, l, l == top);
+            else if (h->variant == 1 || kmax > 31)   // thread-per-point reference kernel (and very large windows)
                 k_lk_track<<<tgrid, 128, 0, st>>>(L.img[0], L.img[1], L.deriv, h->next_pts, L.w, L.h, h->gw, h->gh,
                                                   h->step, h->win, l, l == top);
             else if (kmax <= 8) TF_LKW(8);
