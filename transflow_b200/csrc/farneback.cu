@@ -1160,7 +1160,7 @@ static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int var
             int e = big ? fb_iterate_half<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, 24, st)
                         : fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st);
             if (e) return e;
-        } else if (variant == 23 || variant == 24) {
+        } else if (variant >= 23 && variant <= 24) {
             const bool big = (size_t)L.w * L.h >= (size_t)400000;
             int e = big ? fb_iterate_half<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, variant, st)
                         : fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st);
