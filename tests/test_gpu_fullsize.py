@@ -77,9 +77,11 @@ def test_c2_sum_layer_1080p_bit_exact():
 
 
 # ---- C3: the kernel the bench times, k_moveref_fast<RESET_RANDOM, 3>, pinned to the reference semantics ----------
-@pytest.mark.parametrize("shape", [(270, 484), (2160, 3840)])
-def test_c3_moveref_fast_random_reset_bit_exact_with_philox_fed_oracle(shape, tmp_path):
-    """The single-source fast kernel only runs with DEVICE draws (Philox4x32-7).  The oracle layer is fed the same
+@pytest.mark.parametrize("shape,classname", [((270, 484), "moveref"), ((2160, 3840), "moveref"), ((270, 484), "sum"),
+                                             ((1080, 1920), "sum")])
+def test_c3_moveref_fast_random_reset_bit_exact_with_philox_fed_oracle(shape, classname, tmp_path):
+    """(`sum`: the same fast kernel specialised for the sum layer, C2's layer.)
+    The single-source fast kernel only runs with DEVICE draws (Philox4x32-7).  The oracle layer is fed the same
     numbers through the NumPy restatement of the generator (oracle/philox_np.py, pinned by Random123's known
     answers), so state and frames must be bit-exact with the reference's `r < factor * reset_mask` rule
     (reference.py:58-67)."""
@@ -94,12 +96,12 @@ def test_c3_moveref_fast_random_reset_bit_exact_with_philox_fed_oracle(shape, tm
     pix = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
     mask_png = str(tmp_path / "m.png")
     PIL.Image.fromarray(np.rint(radial_mask(h, w) * 255).astype(np.uint8)).save(mask_png)
-    comp = Compositor.from_args(h, w, [LayerConfig(0, "moveref", reset_mode="random", reset_random_factor=0.5,
+    comp = Compositor.from_args(h, w, [LayerConfig(0, classname, reset_mode="random", reset_random_factor=0.5,
                                                    reset_mask=mask_png)], background_color="#204060", seed=5)
     layer = comp.layers[0]
     assert layer.reset_rng == "device"
     comp.set_sources({0: [PixmapSourceInterface(StillQueue(dev(pix)), np.ones((h, w), bool))]})
-    ora = CN.LayerOracle(CN.LayerSpec(reset_mode="random", reset_random_factor=0.5), h, w,
+    ora = CN.LayerOracle(CN.LayerSpec(classname=classname, reset_mode="random", reset_random_factor=0.5), h, w,
                          intro_masks=[np.ones((h, w), bool)], reset_mask=load_float_mask(mask_png))
     bg = np.empty((h, w, 3), np.uint8)
     bg[:, :] = (0x20, 0x40, 0x60)

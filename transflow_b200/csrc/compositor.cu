@@ -357,7 +357,9 @@ struct FastParams {
     int* err;
 };
 
-template <int RESET, int CHAN>
+// SUM: the same kernel for the `sum` layer (sum.py:9-10) -- no gather, the record of the pixel itself moves by
+// floor(flow) (x to the ROW index, quirk Q8), in place (old == out); the reset, remap and composite stages are shared.
+template <int RESET, int CHAN, bool SUM = false>
 __global__ void __launch_bounds__(256) k_moveref_fast(FastParams P) {
     const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (p0 >= P.n) return;
@@ -368,22 +370,31 @@ __global__ void __launch_bounds__(256) k_moveref_fast(FastParams P) {
         f[0] = make_float2(a.x, a.y); f[1] = make_float2(a.z, a.w);
         f[2] = make_float2(b.x, b.y); f[3] = make_float2(b.z, b.w);
     }
-    int q[4];
-    bool moved[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int off = __float2int_rn(f[k].y) * P.w + __float2int_rn(f[k].x);
-        moved[k] = off != 0;
-        q[k] = moved[k] ? wrap_index(p0 + k + off, P.n, p0 + k, P.err) : p0 + k;
-    }
     int4 rec[4];
+    if (SUM) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) rec[k] = __ldg(P.old + q[k]);
+        for (int k = 0; k < 4; k++) {
+            rec[k] = P.out[p0 + k];          // in place: plain loads, not the read-only path
+            rec[k].x += (int)floorf(f[k].x);
+            rec[k].y += (int)floorf(f[k].y);
+        }
+    } else {
+        int q[4];
+        bool moved[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        // a transparent source does not move (movement.py:34-35): keep the pixel's own record
-        if (moved[k] && rec[k].z == 0) rec[k] = __ldg(P.old + p0 + k);
-        else if (moved[k]) rec[k].z = 1;
+        for (int k = 0; k < 4; k++) {
+            int off = __float2int_rn(f[k].y) * P.w + __float2int_rn(f[k].x);
+            moved[k] = off != 0;
+            q[k] = moved[k] ? wrap_index(p0 + k + off, P.n, p0 + k, P.err) : p0 + k;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) rec[k] = __ldg(P.old + q[k]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            // a transparent source does not move (movement.py:34-35): keep the pixel's own record
+            if (moved[k] && rec[k].z == 0) rec[k] = __ldg(P.old + p0 + k);
+            else if (moved[k]) rec[k].z = 1;
+        }
     }
     if (RESET == TF_RESET_RANDOM) {
         int y = p0 / P.w, x = p0 - y * P.w;
@@ -802,9 +813,30 @@ extern "C" int tf_layer_update(tf_layer* l, const float* flow, const tf_pixmap* 
             TF_LAUNCHED();
             l->cur ^= 1;
         } else if (kind == TF_LAYER_SUM) {
+            const tf_layer_config& c = l->cfg;
+            // single source, no alpha mask, reset off or random with device draws, fused single layer: the fast kernel
+            bool fast = n_pixmaps == 1 && !l->mask_alpha &&
+                        (c.reset_mode == TF_RESET_OFF || (c.reset_mode == TF_RESET_RANDOM && !random && !c.reset_source)) &&
+                        rgb_inout && first_layer && (P.n & 3) == 0 && ((uintptr_t)flow & 15) == 0 &&
+                        ((uintptr_t)l->reset_scale & 15) == 0;
             {
                 ScopedKernelTimer timer(TFK_COMPOSITOR_LAYER, st);
-                k_reference_layer<TF_LAYER_SUM><<<blocks4, 256, 0, st>>>(P);
+                if (fast) {
+                    FastParams F;
+                    F.flow = P.flow; F.old = P.old; F.out = P.out; F.rgba = P.rgba; F.reset_scale = l->reset_scale;
+                    F.reset_factor = c.reset_random_factor; F.pix = P.pix[0]; F.rgb = rgb_inout; F.bg = background_rgb;
+                    F.h = P.h; F.w = P.w; F.n = P.n; F.seed = P.seed; F.frame = P.frame; F.err = P.err;
+                    bool rnd = c.reset_mode == TF_RESET_RANDOM;
+                    if (P.chan[0] == 4) {
+                        if (rnd) k_moveref_fast<TF_RESET_RANDOM, 4, true><<<blocks4, 256, 0, st>>>(F);
+                        else k_moveref_fast<TF_RESET_OFF, 4, true><<<blocks4, 256, 0, st>>>(F);
+                    } else {
+                        if (rnd) k_moveref_fast<TF_RESET_RANDOM, 3, true><<<blocks4, 256, 0, st>>>(F);
+                        else k_moveref_fast<TF_RESET_OFF, 3, true><<<blocks4, 256, 0, st>>>(F);
+                    }
+                } else {
+                    k_reference_layer<TF_LAYER_SUM><<<blocks4, 256, 0, st>>>(P);
+                }
             }
             TF_LAUNCHED();
         } else {
