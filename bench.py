@@ -987,7 +987,14 @@ def run_sharded(args, cfg, rank, world, local):
         chunk_state["next"] = None
         return estimate_chunk(0, n)
     fresh_chunk(K)
-    f_ms = timed(lambda: fresh_chunk(K), 2) / K
+    # F = cost of a pair INSIDE a producer's run of consecutive chunks (no new prepare, lanes not drained): time 4 chunks
+    # that continue one another, as the stream's chunks do
+    cal = {"next": K}
+
+    def continuing_chunk():
+        estimate_chunk(cal["next"], K)
+        cal["next"] += K
+    f_ms = timed(continuing_chunk, 4) / K
     plan = torch.zeros(2, dtype=torch.float64, device="cuda")
     if rank == 0:
         fl = fresh_chunk(1)[0]
@@ -1001,7 +1008,9 @@ def run_sharded(args, cfg, rank, world, local):
     f_ms, a_ms = float(plan[0]), float(plan[1])
     counts = plan_round(world, Q, f_ms, a_ms)
     # rank 0's share counted in pairs and queued beside its accumulation (TFB200_RANK0_PAIRS=chunks: whole chunks first)
-    p0 = plan_rank0_pairs(world, Q, K, f_ms, a_ms) if os.environ.get("TFB200_RANK0_PAIRS", "pairs") == "pairs" else None
+    # (rank 0's estimation shares the SMs with its accumulation and the two do not add up perfectly: keep one pair of slack)
+    p0 = (max(0, plan_rank0_pairs(world, Q, K, f_ms, a_ms) - 1)
+          if os.environ.get("TFB200_RANK0_PAIRS", "pairs") == "pairs" else None)
     transport = os.environ.get("TFB200_TRANSPORT", "p2p")
     frames_per_round = sum(counts) * K if p0 is None else sum(counts[1:]) * K + p0
     fan = None
