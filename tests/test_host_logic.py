@@ -1,6 +1,7 @@
 """Host-side logic that needs no GPU: the video pixmap source (seek / repeat / length bookkeeping of
 ``transflow/pixmap/cv.py``) checked against the REAL reference class where it is importable (the build container),
 and against the expected frame order everywhere."""
+import json
 import os
 import sys
 
@@ -129,3 +130,66 @@ def test_bench_clock_sampler_counts_only_the_timed_region():
     out = s.stop()
     assert len(calls) == 2 and out["samples"] == 2 and out["sm_mhz"] == 1901.5
     assert out["window"].startswith("same load")
+
+
+def test_pipeline_config_round_trip_and_secondary_paths():
+    """``Config.todict`` / ``fromdict`` (checkpoint meta.json, reference config.py:258-323) and the checkpoint /
+    archive path rule ``get_secondary_output_path`` (config.py:325-341)."""
+    from transflow_b200.config import LayerConfig, PixmapSourceConfig
+    from transflow_b200.flow import FlowSource
+    from transflow_b200.flow.sources.cv import CvFlowConfig
+    from transflow_b200.pipeline import Config
+    cfg = Config("clips/a.mp4", mask_path="m.png", cv_config=CvFlowConfig(method="horn-schunck", hs_decay=0.5),
+                 flow_filters="scale=2;clip=1+t", direction="backward", seek_time="0:01.5", duration_time=3,
+                 repeat=2, lock_expr="(1,2)", lock_mode="stay",
+                 pixmap_sources=[PixmapSourceConfig("p.jpg", layers=[0, 1], introduction_path="border:1")],
+                 layers=[LayerConfig(0, "moveref", reset_mode="random", reset_random_factor=0.5), LayerConfig(1, "sum")],
+                 compositor_background="#102030", output_path="out/x-%d.png", size=(640, 360), seed=5,
+                 extra_flow_paths=["b.mp4"], flows_merging_function="sum", view_flow=True, render_scale=0.5,
+                 render_colors="#000,#fff")
+    d = json.loads(json.dumps(cfg.todict()))          # what lands in meta.json
+    back = Config.fromdict(d)
+    assert back.todict() == cfg.todict()
+    assert back.seek_time == 1.5 and back.duration_time == 3 and back.size == (640, 360) and back.seed == 5
+    assert FlowSource.Direction.from_arg(back.direction) == FlowSource.Direction.BACKWARD
+    assert isinstance(back.cv_config, CvFlowConfig) and back.cv_config.hs_decay == 0.5
+    assert back.layers[0].reset_random_factor == 0.5 and back.pixmap_sources[0].layers == [0, 1]
+    assert back.extra_flow_paths == ["b.mp4"] and back.flows_merging_function == "sum" and back.view_flow
+    assert cfg.get_secondary_output_path("_00005.ckpt.zip") == "out/x-%d_00005.ckpt.zip"
+    assert Config("v/clip.flow.zip").get_secondary_output_path(".x") == "v/clip.x"
+    assert Config("v/clip_00012.ckpt.zip").get_secondary_output_path(".y") == "v/clip_00012.y"
+    assert Config("v/clip.mp4", output_path="o/r.001.mp4").get_secondary_output_path(".flow.zip") == "o/r.flow.zip"
+    ref_root = "/root/reference"
+    if os.path.isdir(ref_root):                        # same rule as the reference's own Config
+        import importlib
+        sys.path.insert(0, ref_root)
+        try:
+            RC = importlib.import_module("transflow.config").Config
+            for flow, out in (("v/clip.mp4", "o/r.001.mp4"), ("v/clip.flow.zip", None), ("a/b.mp4", "out/x-%d.png")):
+                assert (Config(flow, output_path=out).get_secondary_output_path("_s.zip")
+                        == RC(flow, output_path=out).get_secondary_output_path("_s.zip"))
+        finally:
+            sys.path.remove(ref_root)
+
+
+def test_polar_expressions_run_numpy_functions_on_tensors():
+    """Inside a ``polar`` filter ``numpy.f(a)`` with a tensor argument runs as ``torch.f`` (the reference hands the
+    expressions NumPy arrays, filters.py:79-84); constants and scalar calls stay NumPy; unknown functions fall back to
+    host evaluation in ``PolarFlowFilter.apply``."""
+    import torch
+    from transflow_b200.flow.filters import PolarFlowFilter, _DeviceNumpy
+    from transflow_b200.utils import parse_lambda_expression
+    a = torch.linspace(-3, 3, 7)
+    npm = _DeviceNumpy()
+    assert torch.allclose(npm.sin(a), torch.sin(a)) and torch.allclose(npm.arctan2(a, a + 1), torch.atan2(a, a + 1))
+    assert torch.allclose(npm.maximum(a, 0.5), torch.clamp(a, min=0.5)) and npm.pi == np.pi and npm.sqrt(4.0) == 2.0
+    f = parse_lambda_expression("r*(1+numpy.abs(numpy.sin(a))) + numpy.pi*t", ("t", "r", "a"), numpy_module=npm)
+    assert torch.allclose(f(0.5, a, a), a * (1 + torch.abs(torch.sin(a))) + np.pi * 0.5)
+    # a function torch does not have: the filter evaluates on host copies, like the reference
+    flow = torch.stack([torch.linspace(-2, 2, 12).reshape(3, 4), torch.linspace(1, 3, 12).reshape(3, 4)], dim=-1).clone()
+    want = flow.clone().numpy()
+    r, th = np.linalg.norm(want.reshape(-1, 2), axis=1).reshape(3, 4), np.arctan2(want[..., 1], want[..., 0])
+    nr = np.unwrap(th) * 0 + r * 2
+    want[..., 1], want[..., 0] = nr * np.sin(th + 0.25), nr * np.cos(th + 0.25)
+    PolarFlowFilter(("numpy.unwrap(a)*0 + r*2", "a+t")).apply(flow, 0.25)
+    np.testing.assert_allclose(flow.numpy(), want, atol=1e-5)
