@@ -878,13 +878,27 @@ def run_sharded(args, cfg, rank, world, local):
     posts = [ops.PostProcess(H, W, forward=forward) for _ in range(lanes)]
     lane_streams = [torch.cuda.Stream() for _ in range(lanes)] if lanes > 1 else None
     est_main = torch.cuda.Stream()
+    # hand-off of a finished flow to rank 0: "store" = the post-process gather kernel stores straight into rank 0's
+    # ring over NVLink (the kernel then runs at NVLink speed on the lane); "copy" = post-process locally, then a
+    # copy-engine transfer on a side stream while the lane already solves the next pair
+    handoff = os.environ.get("TFB200_HANDOFF", "copy")
+    copy_streams = [torch.cuda.Stream() for _ in range(lanes)]
+    peer_views = {}
+
+    def peer_view(address):
+        from transflow_b200.peer import raw_tensor
+        if address not in peer_views:
+            peer_views[address] = raw_tensor(address, (H, W, 2))
+        return peer_views[address]
     chunk_state = {"next": None}
 
     def join_lanes():
+        main = torch.cuda.current_stream()
         if lane_streams:
-            main = torch.cuda.current_stream()
             for s in lane_streams:
                 main.wait_stream(s)
+        for s in copy_streams:
+            main.wait_stream(s)
 
     def estimate_chunk(first_pair, n_pairs, outs=None, gate=None, join=True):
         """n_pairs consecutive pairs: that many solves + post-processes, and one extra prepare when the chunk does
@@ -922,7 +936,18 @@ def run_sharded(args, cfg, rank, world, local):
                 if io["host"]:
                     feeder.release()
                 flow.record_stream(main)
-                flows.append(posts[lane](flow, None if outs is None else outs[i]))
+                if outs is None or handoff == "store":
+                    flows.append(posts[lane](flow, None if outs is None else outs[i]))
+                else:
+                    posts[lane](flow)
+                    done = torch.cuda.Event()
+                    done.record()
+                    cs = copy_streams[lane]
+                    with torch.cuda.stream(cs):
+                        cs.wait_event(done)
+                        peer_view(outs[i]).copy_(flow, non_blocking=True)
+                        flow.record_stream(cs)
+                    flows.append(outs[i])
         chunk_state["next"] = first_pair + n_pairs
         if join:
             join_lanes()
@@ -1130,11 +1155,14 @@ def run_sharded(args, cfg, rank, world, local):
             "config": workload_config(cfg, dict(
                 sharding=(f"chunks of {K} pairs; per round {counts} chunks per rank" if p0 is None else
                           f"chunks of {K} pairs; per round {counts[1:]} chunks per producer rank and {p0} pairs on rank 0, "
-                          "queued beside its accumulation") +
+                          "queued one round ahead beside its accumulation") +
                          f" (rank 0 also runs the sequential accumulate+remap); {rounds_per_step} rounds per step; "
                          f"transport {transport}: "
-                         + ("the producer's last post-process kernel stores the flow into rank 0's ring over NVLink "
-                            "peer memory, counters + cuStreamWaitValue32 order it" if transport == "p2p" else
+                         + (("the producer's last post-process kernel stores the flow into rank 0's ring over NVLink "
+                             "peer memory" if handoff == "store" else
+                             "a copy-engine transfer moves the post-processed flow into rank 0's ring over NVLink peer "
+                             "memory while the lane solves the next pair") +
+                            ", counters + cuStreamWaitValue32 order it" if transport == "p2p" else
                             "batched NCCL send/recv, receives posted one round ahead"),
                 frames_per_step=stream.frames_per_round * rounds_per_step, state_check=check,
                 calibrated_ms={"flow_per_pair": f_ms, "accumulate_per_frame": a_ms},

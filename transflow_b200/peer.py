@@ -50,6 +50,15 @@ class DeviceBuffer:
             self.address = 0
 
 
+def raw_tensor(address: int, shape, dtype=torch.float32) -> torch.Tensor:
+    """A tensor view of raw device memory at ``address`` (local, or peer memory mapped through CUDA IPC): what
+    ``Tensor.copy_`` needs to move a buffer with the copy engines instead of a kernel."""
+    n = int(torch.tensor([], dtype=dtype).element_size())
+    for s in shape:
+        n *= int(s)
+    return torch.as_tensor(_RawArray(int(address), n), device="cuda").view(dtype).view(*shape)
+
+
 def open_ipc(handle: bytes) -> int:
     p = C.c_void_p()
     buf = (C.c_uint8 * 64).from_buffer_copy(handle)
