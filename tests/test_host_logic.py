@@ -193,3 +193,29 @@ def test_polar_expressions_run_numpy_functions_on_tensors():
     want[..., 1], want[..., 0] = nr * np.sin(th + 0.25), nr * np.cos(th + 0.25)
     PolarFlowFilter(("numpy.unwrap(a)*0 + r*2", "a+t")).apply(flow, 0.25)
     np.testing.assert_allclose(flow.numpy(), want, atol=1e-5)
+
+
+def test_gradient_pixmap_tree_draws_match_reference():
+    """``GradientPixmapSource.generate`` is written as its own grammar; a seeded run must consume ``random`` exactly
+    as the reference does (still.py:94-118) so that a given seed paints the same picture."""
+    import random
+    ref_root = "/root/reference"
+    if not os.path.isdir(ref_root):
+        pytest.skip("the reference tree is only present in the build container")
+    import importlib
+    from transflow_b200.pixmap.still import GradientPixmapSource as G
+    sys.path.insert(0, ref_root)
+    try:
+        R = importlib.import_module("transflow.pixmap.still").GradientPixmapSource
+        for seed in range(12):
+            for depth in (0, 1, 2, 4):
+                for kind in (G.NODE_MIX, G.NODE_TRIPLE, G.NODE_Z, G.NODE_B):
+                    random.seed(seed)
+                    mine = G.generate(G.__new__(G), kind, depth)
+                    random.seed(seed)
+                    theirs = R.generate(R.__new__(R), kind, depth)
+                    assert mine == theirs, (seed, depth, kind)
+    finally:
+        sys.path.remove(ref_root)
+    with pytest.raises(ValueError):
+        G.generate(G.__new__(G), 99, 2)

@@ -88,24 +88,40 @@ class GradientPixmapSource(StillPixmapSource):
 
     NODE_I, NODE_J, NODE_RGB, NODE_MIX, NODE_TRIPLE, NODE_Z, NODE_B = range(7)
 
+    # The tree grammar of the reference (still.py:94-118), written as three mutually recursive productions.  A
+    # seeded run must issue the same `random.random()` calls in the same order to give the same picture:
+    #   inner(kind, d)  = leaf                      if d <= 0      (kind: MIX or TRIPLE)
+    #                   = (kind, operand(d-1) x 3)  otherwise, operands left to right
+    #   operand(d)      = leaf                      if d <= 0      (no draw)
+    #                   = leaf if draw < 1/4 else inner(MIX, d-1)
+    #   leaf            = I if draw < .333, J if draw < .666, else RGB with three more draws in [-1, 1)
+    def _leaf(self) -> tuple:
+        pick = random.random()
+        if pick < .333:
+            return (self.NODE_I, None, None, None)
+        if pick < .666:
+            return (self.NODE_J, None, None, None)
+        channels = [random.random() * 2 - 1 for _ in range(3)]
+        return (self.NODE_RGB, *channels)
+
+    def _operand(self, depth: int) -> tuple:
+        if depth <= 0 or random.random() < .25:
+            return self._leaf()
+        return self._inner(self.NODE_MIX, depth - 1)
+
+    def _inner(self, kind: int, depth: int) -> tuple:
+        if depth <= 0:
+            return self._leaf()
+        return (kind, *[self._operand(depth - 1) for _ in range(3)])
+
     def generate(self, node_type: int, depth: int) -> tuple:
-        if depth <= 0 and node_type != self.NODE_Z:
-            return self.generate(self.NODE_Z, 0)
         if node_type in (self.NODE_TRIPLE, self.NODE_MIX):
-            return (node_type, self.generate(self.NODE_B, depth - 1), self.generate(self.NODE_B, depth - 1),
-                    self.generate(self.NODE_B, depth - 1))
+            return self._inner(node_type, depth)
         if node_type == self.NODE_B:
-            if random.random() < .25:
-                return self.generate(self.NODE_Z, depth - 1)
-            return self.generate(self.NODE_MIX, depth - 1)
+            return self._operand(depth)
         if node_type == self.NODE_Z:
-            x = random.random()
-            if x < .333:
-                return (self.NODE_I, None, None, None)
-            if x < .666:
-                return (self.NODE_J, None, None, None)
-            return (self.NODE_RGB, random.random() * 2 - 1, random.random() * 2 - 1, random.random() * 2 - 1)
-        raise ValueError(f"Unkown node type {node_type}")
+            return self._leaf()
+        raise ValueError(f"Unknown node type {node_type}")
 
     def evaluate(self, tree: tuple, i, j):
         """-> three float64 arrays (or scalars) for channel r, g, b."""
