@@ -314,6 +314,25 @@ def test_farneback_staged_kernel_is_bit_identical_to_default(variant):
         assert mean <= 0.01 and mx <= 0.1, (mean, mx)
 
 
+@pytest.mark.parametrize("shape", [(603, 812), (1000, 1284), (720, 1282)])
+def test_ring_and_default_kernels_ragged_sizes(shape):
+    """Ragged strips / chunks (width not a multiple of 64, height not a multiple of 14, last chunk of a few rows) and a
+    width that is not a multiple of 4 (the ring kernels then hand over to the half-buffer kernel): the ring variants
+    and the 128-column configuration stay bit-identical to the default, on small and on large motion, several times
+    over (a race between the tensor copies and the taps would not repeat)."""
+    from transflow_b200 import ops
+    h, w = shape
+    g0, g1 = clip_pair(h, w, seed=13)
+    for right in (g1, np.roll(g0, (-11, 17), (0, 1))):
+        want = ops.Farneback(h, w, variant=8)(dev(g0), dev(right))
+        mean, mx = epe(want.cpu().numpy(), F.farneback(g0, right))
+        assert mean <= 0.01 and mx <= 0.1, (mean, mx)
+        for variant in (19, 21, 23):
+            fb = ops.Farneback(h, w, variant=variant)
+            for rep in range(3):
+                assert torch.equal(fb(dev(g0), dev(right)), want), (variant, rep)
+
+
 @pytest.mark.parametrize("shape,params", [((270, 484), dict()), ((540, 960), dict(poly_n=7, poly_sigma=1.5)),
                                           ((200, 333), dict(poly_n=3, poly_sigma=0.9))])
 def test_farneback_folded_expansion_matches_two_stage(shape, params):
