@@ -1053,7 +1053,7 @@ def run_sharded(args, cfg, rank, world, local):
             lo = (j - e2e_first_round["j"]) * frames_per_round
             fan.expect(sum(1 for i in range(lo, lo + frames_per_round) if i % world == rank))
     stream = ShardedFlowStream(rank, world, K, counts, estimate_chunk, accumulate, (H, W, 2), "cuda",
-                               transport=transport, round_hook=round_hook, rank0_pairs=p0, join=join_lanes)
+                               transport=transport, round_hook=round_hook, rank0_pairs=p0)
     chunk_state["next"] = None
     # rounds per step so that one step lasts about as long as a single-GPU step
     rounds_per_step = max(1, int(round(cfg["frames_per_step"] * world / frames_per_round)))

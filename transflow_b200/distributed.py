@@ -73,13 +73,12 @@ class ShardedFlowStream:
     """
 
     def __init__(self, rank, world, chunk_pairs, counts, estimate_chunk, accumulate, flow_shape, device,
-                 group=None, transport="nccl", round_hook=None, rank0_pairs=None, join=None):
+                 group=None, transport="nccl", round_hook=None, rank0_pairs=None):
         self.rank, self.world, self.k = rank, world, chunk_pairs
         self.transport = transport
         self.round_hook = round_hook      # called on every rank with the round index before the round starts
         self.counts = list(counts)
         self.rank0_pairs = rank0_pairs
-        self.join = join                  # (unused: chunks queued with join=False carry their own ready())
         if rank0_pairs is None:
             self.slots = [(owner, chunk_pairs) for owner in round_slots(self.counts)]
         else:
