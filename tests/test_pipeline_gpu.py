@@ -162,3 +162,51 @@ def test_level_a_reference_pipeline_runs_with_swapped_classes(tmp_path):
     for t, (a, b) in enumerate(zip(outs["stock"], outs["swapped"])):
         assert a.shape == (h, w, 3)
         np.testing.assert_array_equal(a, b, err_msg=f"frame {t}")
+
+
+def test_plugin_errors_are_the_reference_exceptions(tmp_path):
+    """SURVEY.md 8(b) error contract: the exceptions the reference raises at the same places (cv.py:474-476, 518;
+    source.py:313, 294-295; layer.py:55; NumPy's IndexError for a flow that points outside the frame)."""
+    from transflow_b200 import ops
+    from transflow_b200.compositor import Compositor
+    from transflow_b200.compositor.pixmap_source_interface import PixmapSourceInterface, StillQueue
+    from transflow_b200.config import LayerConfig
+    from transflow_b200.flow import FlowSource
+    from transflow_b200.flow.sources.cv import ArrayCapture, CvFlowConfig, CvFlowSource
+    from transflow_b200.synthetic import synthetic_clip
+    h, w = 48, 64
+    clip = synthetic_clip(h, w, 3, seed=1)
+    with pytest.raises(ValueError):
+        CvFlowSource.Method.from_string("block-matching")
+    with pytest.raises(ValueError):
+        FlowSource.Direction.from_arg("sideways")
+    with pytest.raises(TypeError):
+        CvFlowConfig(fb_window=15)                               # unknown field
+    with pytest.raises(ImportError):                             # LiteFlowNet is outside the accelerated path
+        with FlowSource.from_args(ArrayCapture(clip), cv_config=CvFlowConfig(method="liteflownet")) as src:
+            next(src)
+    with pytest.raises(RuntimeError):                            # locked before any flow exists (source.py:313)
+        with FlowSource.from_args(ArrayCapture(clip), lock_expr="(0,1),(100,1)", lock_mode="stay") as src:
+            next(src)
+    with FlowSource.from_args(ArrayCapture(clip), direction="backward") as src:
+        assert len(list(src)) == 2
+        with pytest.raises(StopIteration):
+            next(src)
+    with pytest.raises(ValueError):
+        Compositor.from_args(h, w, [LayerConfig(0, "hologram")])
+    with pytest.raises(ValueError):
+        ops.Farneback(h, w)(torch.zeros((h, w + 1), dtype=torch.uint8, device="cuda"),
+                            torch.zeros((h, w), dtype=torch.uint8, device="cuda"))
+    comp = Compositor.from_args(h, w, [LayerConfig(0, "moveref")])
+    comp.set_sources({0: [PixmapSourceInterface(StillQueue(np.zeros((h, w, 3), np.uint8)), np.ones((h, w), bool))]})
+    with pytest.raises(ValueError):
+        comp.step(np.zeros((h, w + 2, 2), np.float32))           # flow of another size
+    flow = np.zeros((h, w, 2), np.float32)
+    flow[h - 1, w - 1] = (3, 2)                                   # un-clipped: points past the last pixel
+    comp.step(flow)
+    with pytest.raises(IndexError):                              # NumPy's .flat[] would have raised in the reference
+        comp.layers[0].check_indices()
+    bad = Compositor.from_args(h, w, [LayerConfig(0, "moveref")])
+    bad.set_sources({0: [PixmapSourceInterface(StillQueue(np.zeros((h + 1, w, 3), np.uint8)), np.ones((h, w), bool))]})
+    with pytest.raises(ValueError):
+        bad.step(np.zeros((h, w, 2), np.float32))                # pixmap of another size
