@@ -1093,7 +1093,7 @@ def run_sharded(args, cfg, rank, world, local):
         def state_sum(c):
             total = 0
             for layer in c.layers:
-                d = layer.data
+                d = None if getattr(layer, "KIND", None) == "static" else layer.data   # (a static layer has no map)
                 if d is not None:
                     total += int(torch.from_numpy(np.ascontiguousarray(d)).long().sum())
                 total += int(torch.from_numpy(np.ascontiguousarray(layer.rgba)).long().sum())
