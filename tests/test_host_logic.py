@@ -174,8 +174,8 @@ def test_pipeline_config_round_trip_and_secondary_paths():
 
 def test_polar_expressions_run_numpy_functions_on_tensors():
     """Inside a ``polar`` filter ``numpy.f(a)`` with a tensor argument runs as ``torch.f`` (the reference hands the
-    expressions NumPy arrays, filters.py:79-84); constants and scalar calls stay NumPy; unknown functions fall back to
-    host evaluation in ``PolarFlowFilter.apply``."""
+    expressions NumPy arrays, filters.py:79-84); constants and scalar calls stay NumPy; a function torch does not have
+    raises unless host evaluation of the user's lambda is switched on explicitly."""
     import torch
     from transflow_b200.flow.filters import PolarFlowFilter, _DeviceNumpy
     from transflow_b200.utils import parse_lambda_expression
@@ -191,7 +191,11 @@ def test_polar_expressions_run_numpy_functions_on_tensors():
     r, th = np.linalg.norm(want.reshape(-1, 2), axis=1).reshape(3, 4), np.arctan2(want[..., 1], want[..., 0])
     nr = np.unwrap(th) * 0 + r * 2
     want[..., 1], want[..., 0] = nr * np.sin(th + 0.25), nr * np.cos(th + 0.25)
-    PolarFlowFilter(("numpy.unwrap(a)*0 + r*2", "a+t")).apply(flow, 0.25)
+    flt = PolarFlowFilter(("numpy.unwrap(a)*0 + r*2", "a+t"))
+    with pytest.raises(NotImplementedError):          # no silent host path
+        flt.apply(flow.clone(), 0.25)
+    flt.allow_host_expressions = True                  # explicit opt-in: only the user's lambda runs on the host
+    flt.apply(flow, 0.25)
     np.testing.assert_allclose(flow.numpy(), want, atol=1e-5)
 
 

@@ -6,6 +6,8 @@ NumPy's promotion rules reproduced (a Python scalar keeps float32 arithmetic, a 
 ``polar`` evaluates arbitrary user expressions of per-pixel arrays ``(r, a)``: those run as device tensor
 expressions between two kernel calls.
 """
+import os
+
 import torch
 
 from .. import ops
@@ -93,7 +95,12 @@ class _DeviceNumpy:
 class PolarFlowFilter(FlowFilter):
     """Polar re-parametrisation with user expressions of ``(t, r, a)`` arrays (filters.py:73-87).  The expressions
     are arbitrary Python: they run on the device tensors when they are made of operators and ``numpy`` functions
-    torch also has, and on host copies of ``r`` and ``a`` (the reference's own evaluation) when they are not."""
+    torch also has.  An expression that needs anything else raises (there is no silent host path); setting
+    ``PolarFlowFilter.allow_host_expressions = True`` (or ``TRANSFLOW_B200_POLAR_HOST_EXPR=1``) lets exactly the user's
+    lambda -- nothing of this package's arithmetic -- be evaluated on host copies of ``r`` and ``a``, as the reference
+    evaluates it."""
+
+    allow_host_expressions = os.environ.get("TRANSFLOW_B200_POLAR_HOST_EXPR", "0") == "1"
 
     def __init__(self, args):
         self.exprs = [parse_lambda_expression(a, ("t", "r", "a"), numpy_module=_DeviceNumpy()) for a in args]
@@ -106,7 +113,11 @@ class PolarFlowFilter(FlowFilter):
         try:
             new_radius = self.expr_radius(t, radius, theta)
             new_theta = self.expr_theta(t, radius, theta)
-        except (NotImplementedError, TypeError, RuntimeError, ValueError, AttributeError):
+        except (NotImplementedError, TypeError, RuntimeError, ValueError, AttributeError) as err:
+            if not self.allow_host_expressions:
+                raise NotImplementedError(
+                    f"polar filter expression cannot run on device tensors ({err}); use operators and numpy functions "
+                    "torch also provides, or set PolarFlowFilter.allow_host_expressions = True") from err
             r, a = radius.cpu().numpy(), theta.cpu().numpy()
             new_radius, new_theta = (e(t, r, a) for e in self.host_exprs)
 
