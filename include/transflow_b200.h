@@ -62,6 +62,10 @@ TF_API int tf_timer_read(int tag, double* total_ms, uint64_t* launches);
 
 /* ---- frame prep: cv2.cvtColor(BGR2GRAY) at transflow/flow/sources/cv.py:465 ------------- */
 TF_API int tf_gray_from_bgr(const uint8_t* bgr, uint8_t* gray, int height, int width, void* stream);
+/* cv2.resize(frame, (width, height), interpolation=cv2.INTER_NEAREST) of a BGR u8 frame
+ * (transflow/flow/sources/cv.py:464, :455-457), bit-exact: source index min(floor(x / (dw / sw)), sw - 1). */
+TF_API int tf_resize_nearest_bgr(const uint8_t* src, int src_height, int src_width, uint8_t* dst, int height, int width,
+                                 void* stream);
 
 /* ---- Farneback: cv2.calcOpticalFlowFarneback at transflow/flow/sources/cv.py:477-490 ----- */
 typedef struct tf_farneback tf_farneback;

@@ -210,3 +210,45 @@ def test_plugin_errors_are_the_reference_exceptions(tmp_path):
     bad.set_sources({0: [PixmapSourceInterface(StillQueue(np.zeros((h + 1, w, 3), np.uint8)), np.ones((h, w), bool))]})
     with pytest.raises(ValueError):
         bad.step(np.zeros((h, w, 2), np.float32))                # pixmap of another size
+
+
+@pytest.mark.parametrize("src,dst", [((480, 854), (270, 480)), ((270, 480), (1080, 1920)), ((123, 457), (77, 301)),
+                                      ((96, 128), (96, 128)), ((2160, 3840), (1080, 1920))])
+def test_resize_nearest_bit_exact(src, dst):
+    """cv2.resize(frame, (w, h), interpolation=INTER_NEAREST) as the reference calls it (cv.py:464), on the device."""
+    import cv2
+    from transflow_b200 import ops
+    rng = np.random.default_rng(31)
+    frame = rng.integers(0, 256, (*src, 3), dtype=np.uint8)
+    got = ops.resize_nearest_bgr(torch.from_numpy(frame).cuda(), dst[0], dst[1]).cpu().numpy()
+    np.testing.assert_array_equal(got, cv2.resize(frame, dsize=(dst[1], dst[0]), interpolation=cv2.INTER_NEAREST))
+
+
+def test_flow_source_resizes_frames_of_another_size_on_device():
+    """A capture that delivers frames of another size than it reports (a webcam ignoring set(), cv.py:455-457): the
+    source resizes with INTER_NEAREST like the reference, here after the upload."""
+    import cv2
+    from oracle import flow_cv as F
+    from transflow_b200.flow import FlowSource
+    from transflow_b200.flow.sources.cv import ArrayCapture
+    from transflow_b200.synthetic import synthetic_clip
+    big = synthetic_clip(192, 256, 3, seed=8)
+
+    class Lying(ArrayCapture):
+        def get(self, prop):
+            if prop == cv2.CAP_PROP_FRAME_WIDTH:
+                return 128
+            if prop == cv2.CAP_PROP_FRAME_HEIGHT:
+                return 96
+            return super().get(prop)
+
+    with FlowSource.from_args(Lying(big), direction="backward") as src:
+        assert (src.width, src.height) == (128, 96)
+        flows = list(src)
+    small = [cv2.resize(f, dsize=(128, 96), interpolation=cv2.INTER_NEAREST) for f in big]
+    grays = [F.gray_from_bgr(f) for f in small]
+    assert len(flows) == 2
+    for t, got in enumerate(flows):
+        want = F.post_process(F.farneback(grays[t + 1], grays[t]), False)
+        err = np.linalg.norm(got - want, axis=-1)
+        assert err.mean() <= 0.01 and err.max() <= 0.1, (t, err.mean(), err.max())

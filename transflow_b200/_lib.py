@@ -69,6 +69,7 @@ SIGNATURES = {
     "tf_timer_enable": (_i, [_i]),
     "tf_timer_read": (_i, [_i, C.POINTER(_d), C.POINTER(_u64)]),
     "tf_gray_from_bgr": (_i, [_vp, _vp, _i, _i, _vp]),
+    "tf_resize_nearest_bgr": (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),
     "tf_farneback_create": (_i, [C.POINTER(_vp), _i, _i, _d, _i, _i, _i, _i, _d, _i, _i]),
     "tf_farneback_destroy": (_i, [_vp]),
     "tf_farneback_prepare": (_i, [_vp, _i, _vp, _vp]),

@@ -143,6 +143,34 @@ extern "C" int tf_gray_from_bgr(const uint8_t* bgr, uint8_t* gray, int height, i
     return TF_OK;
 }
 
+// cv2.resize(frame, dsize, interpolation=INTER_NEAREST) of a BGR frame (flow/sources/cv.py:464): OpenCV's resizeNN takes
+// source column min(floor(x * ifx), sw - 1) with ifx = 1 / (dw / sw) in double, and the same for rows.
+__global__ void __launch_bounds__(256) k_resize_nearest_c3(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                           int sh, int sw, int dh, int dw, double ifx, double ify) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dw) return;
+    const int sx = min(__double2int_rd((double)x * ifx), sw - 1);
+    const int sy = min(__double2int_rd((double)y * ify), sh - 1);
+    const uint8_t* p = src + ((size_t)sy * sw + sx) * 3;
+    uint8_t* q = dst + ((size_t)y * dw + x) * 3;
+    q[0] = __ldg(p);
+    q[1] = __ldg(p + 1);
+    q[2] = __ldg(p + 2);
+}
+
+extern "C" int tf_resize_nearest_bgr(const uint8_t* src, int src_height, int src_width, uint8_t* dst, int height, int width,
+                                     void* stream) {
+    TF_REQUIRE(src && dst, TF_ERR_INVALID_ARG, "tf_resize_nearest_bgr: null buffer");
+    TF_REQUIRE(src_height > 0 && src_width > 0 && height > 0 && width > 0, TF_ERR_SHAPE,
+               "tf_resize_nearest_bgr: bad shape %dx%d -> %dx%d", src_width, src_height, width, height);
+    if (int e = require_sm100()) return e;
+    const double ifx = 1.0 / ((double)width / (double)src_width), ify = 1.0 / ((double)height / (double)src_height);
+    k_resize_nearest_c3<<<dim3(ceil_div(width, 256), height), 256, 0, as_stream(stream)>>>(src, dst, src_height, src_width,
+                                                                                          height, width, ifx, ify);
+    TF_LAUNCHED();
+    return TF_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // FlowSource.post_process (flow/sources/source.py:337-363)
 // ------------------------------------------------------------------------------------------

@@ -206,23 +206,30 @@ class CvFlowSource(FlowSource):
             return frame
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream()
+        resize_from = None
         if isinstance(frame, torch.Tensor) and frame.is_pinned():
             src = frame
         else:
             if isinstance(frame, torch.Tensor):
                 frame = frame.numpy()
             if frame.shape[1] != self.width or frame.shape[0] != self.height:
-                import cv2
-                frame = cv2.resize(frame, dsize=(self.width, self.height), interpolation=cv2.INTER_NEAREST)
-            if self._stage is None:
-                self._stage = [torch.empty((self.height, self.width, 3), dtype=torch.uint8).pin_memory()
-                               for _ in range(2)]
-                self._stage_events = [None, None]
-            k = self._stage_index = (getattr(self, "_stage_index", 0) + 1) & 1
-            if self._stage_events[k] is not None:
-                self._stage_events[k].synchronize()     # the previous copy out of this buffer is done
-            self._stage[k].numpy()[...] = frame
-            src = self._stage[k]
+                # the capture delivers another size (cv.py:464 resizes with INTER_NEAREST): upload the frame as it is
+                # and resize on the device
+                resize_from = torch.from_numpy(np.ascontiguousarray(frame)).pin_memory()
+            if resize_from is None:
+                if self._stage is None:
+                    self._stage = [torch.empty((self.height, self.width, 3), dtype=torch.uint8).pin_memory()
+                                   for _ in range(2)]
+                    self._stage_events = [None, None]
+                k = self._stage_index = (getattr(self, "_stage_index", 0) + 1) & 1
+                if self._stage_events[k] is not None:
+                    self._stage_events[k].synchronize()     # the previous copy out of this buffer is done
+                self._stage[k].numpy()[...] = frame
+                src = self._stage[k]
+            else:
+                src = resize_from
+        if tuple(src.shape[:2]) != (self.height, self.width):
+            resize_from = src
         # preallocated ring of device frames (no allocation per frame): a slot is overwritten once the
         # gray conversion that read its previous frame has run
         if self._dev_ring is None:
@@ -237,10 +244,16 @@ class CvFlowSource(FlowSource):
         with torch.cuda.stream(self._copy_stream):
             if self._dev_consumed[slot] is not None:
                 self._copy_stream.wait_event(self._dev_consumed[slot])
-            dev.copy_(src, non_blocking=True)
+            if resize_from is not None:
+                raw = resize_from.cuda(non_blocking=True)       # (rare path: one allocation per frame)
+                ops.resize_nearest_bgr(raw, self.height, self.width, out=dev)
+                raw.record_stream(self._copy_stream)
+                self._keep_pinned = resize_from                  # alive until the next upload
+            else:
+                dev.copy_(src, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
-        if src is not frame and self._stage is not None:
+        if resize_from is None and src is not frame and self._stage is not None:
             self._stage_events[self._stage_index] = ev
         return _Uploaded(dev, ev, slot)
 

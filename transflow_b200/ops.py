@@ -39,6 +39,18 @@ def gray_from_bgr(bgr: torch.Tensor, out: torch.Tensor | None = None) -> torch.T
     return out
 
 
+def resize_nearest_bgr(bgr: torch.Tensor, height: int, width: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """``cv2.resize(frame, (width, height), interpolation=cv2.INTER_NEAREST)`` (flow/sources/cv.py:464), bit-exact."""
+    bgr = _cuda(bgr, torch.uint8, "bgr")
+    if bgr.ndim != 3 or bgr.shape[2] != 3:
+        raise ValueError(f"bgr must be (H, W, 3), got {tuple(bgr.shape)}")
+    if out is None:
+        out = torch.empty((int(height), int(width), 3), dtype=torch.uint8, device=bgr.device)
+    check(_lib.load().tf_resize_nearest_bgr(ptr(bgr), int(bgr.shape[0]), int(bgr.shape[1]), ptr(out), int(height),
+                                            int(width), stream_ptr()))
+    return out
+
+
 class Farneback:
     """Device Farneback flow with the parameters of ``CvFlowConfig.fb_*`` (cv.py:275-281)."""
 
