@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtransflow_b200.so")
+LIB_PATH = os.environ.get("TFB200_LIB") or os.path.join(_HERE, "libtransflow_b200.so")   # (override: A/B of two builds)
 
 TF_OK = 0
 TF_ERR_INVALID_ARG = -1
@@ -160,9 +160,23 @@ def check(status: int):
     raise RuntimeError(msg)
 
 
+_raw_stream = None
+
+
 def stream_ptr():
-    import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """The current torch stream of the current device as a ``cudaStream_t`` (every call of the library takes one).
+    Read through torch's raw accessor: ``torch.cuda.current_stream()`` builds a Python Stream object on every call, and
+    a frame makes a dozen calls."""
+    global _raw_stream
+    if _raw_stream is None:
+        import torch
+        get_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+        get_device = getattr(torch._C, "_cuda_getDevice", None)
+        if get_stream is not None and get_device is not None:
+            _raw_stream = lambda: get_stream(get_device())          # noqa: E731
+        else:
+            _raw_stream = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
+    return C.c_void_p(_raw_stream())
 
 
 def ptr(t):

@@ -276,16 +276,24 @@ __global__ void __launch_bounds__(BR_NT) k_fb_blur_resize(const uint8_t* __restr
     int off = 0;  // column of the footprint's first pixel inside its staged row
     if (c0 >= 0 && ((c0 & ~3) + ((((c0 & 3) + ncols + 3) >> 2) << 2)) <= W && (W & 3) == 0 &&
         (reinterpret_cast<uintptr_t>(gray) & 3) == 0) {
-        // tiles inside the frame: aligned 32-bit loads, one warp per footprint row (the row's address -- a reflection
-        // and a 64-bit multiply -- is computed once per row, not once per word; the flat loop spent a division and
-        // a reflection on every word and made this kernel instruction-bound)
+        // tiles inside the frame: aligned 32-bit loads, four independent requests per thread in flight
         off = c0 & 3;
-        const int nw = (off + ncols + 3) >> 2;
-        const int lane = tid & 31;
-        for (int fr = tid >> 5; fr < nrows; fr += BR_NT / 32) {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(gray + (size_t)reflect101(r0 + fr, H) * W + (c0 - off));
-            uint32_t* dst = reinterpret_cast<uint32_t*>(sS + fr * fc_pitch);
-            for (int q = lane; q < nw; q += 32) dst[q] = __ldg(src + q);
+        const int nw = (off + ncols + 3) >> 2, total = nrows * nw;
+        constexpr int NTH = BR_NT;
+        for (int base = tid; base < total; base += 4 * NTH) {
+            uint32_t v[4];
+            int fr[4], q[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int i = base + k * NTH;
+                fr[k] = i / nw;
+                q[k] = i - fr[k] * nw;
+                if (i < total)
+                    v[k] = __ldg(reinterpret_cast<const uint32_t*>(gray + (size_t)reflect101(r0 + fr[k], H) * W + (c0 - off)) + q[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (base + k * NTH < total) reinterpret_cast<uint32_t*>(sS + fr[k] * fc_pitch)[q[k]] = v[k];
         }
     } else {
         // tiles touching a border: one warp per footprint row, byte loads with reflected columns
@@ -293,11 +301,7 @@ __global__ void __launch_bounds__(BR_NT) k_fb_blur_resize(const uint8_t* __restr
         for (int fr = tid >> 5; fr < nrows; fr += BR_NT / 32) {
             const uint8_t* src = gray + (size_t)reflect101(r0 + fr, H) * W;
             unsigned char* dst = sS + fr * fc_pitch;
-            for (int fc = lane; fc < ncols; fc += 32) {
-                int c = c0 + fc;
-                if ((unsigned)c >= (unsigned)W) c = reflect101(c, W);   // only the few columns outside the frame
-                dst[fc] = __ldg(src + c);
-            }
+            for (int fc = lane; fc < ncols; fc += 32) dst[fc] = __ldg(src + reflect101(c0 + fc, W));
         }
     }
     __syncthreads();
@@ -307,28 +311,18 @@ __global__ void __launch_bounds__(BR_NT) k_fb_blur_resize(const uint8_t* __restr
         const int x = min(x0 + ox, w - 1);
         const int lc = sx[x] - sx[x0];
         const float t = tx[x];
-        // two footprint rows per thread and pass: the tap weights and the loop bookkeeping are shared (they were most
-        // of this loop's instructions); every sum keeps its own accumulation order, so the result is unchanged
-        const int rstep = BR_NT / tw;
-        for (int fr = tid / tw; fr < nrows; fr += 2 * rstep) {
-            const bool two = fr + rstep < nrows;
-            const unsigned char* row0 = sS + fr * fc_pitch + off + lc;
-            const unsigned char* row1 = two ? row0 + rstep * fc_pitch : row0;
-            float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
-            float v0 = (float)row0[0], v1 = (float)row1[0];
-#pragma unroll 4
+        for (int fr = tid / tw; fr < nrows; fr += BR_NT / tw) {
+            const unsigned char* row = sS + fr * fc_pitch + off + lc;
+            float a = 0.f, b = 0.f;
+            float v = (float)row[0];
             for (int j = 0; j < ksz; j++) {
-                const float g = sG[j];
-                const float n0 = (float)row0[j + 1], n1 = (float)row1[j + 1];
-                a0 = fmaf(g, v0, a0);
-                b0 = fmaf(g, n0, b0);
-                a1 = fmaf(g, v1, a1);
-                b1 = fmaf(g, n1, b1);
-                v0 = n0;
-                v1 = n1;
+                float g = sG[j];
+                float nv = (float)row[j + 1];
+                a = fmaf(g, v, a);
+                b = fmaf(g, nv, b);
+                v = nv;
             }
-            sT[fr * tw + ox] = a0 * (1.f - t) + b0 * t;
-            if (two) sT[(fr + rstep) * tw + ox] = a1 * (1.f - t) + b1 * t;
+            sT[fr * tw + ox] = a * (1.f - t) + b * t;
         }
     }
     __syncthreads();
@@ -344,7 +338,6 @@ __global__ void __launch_bounds__(BR_NT) k_fb_blur_resize(const uint8_t* __restr
                 const float* col = sT + lr * tw + ox;
                 float a = 0.f, b = 0.f;
                 float v = col[0];
-#pragma unroll 4
                 for (int j = 0; j < ksz; j++) {
                     float g = sG[j];
                     float nv = col[(j + 1) * tw];
