@@ -255,7 +255,10 @@ def algorithmic_bytes_per_frame(cfg, fb=None) -> float:
     comp = 0.0
     for layer in cfg["layers"]:
         kind = layer["classname"]
-        comp += {"moveref": 46.0, "sum": 30.0, "static": 6.0}[kind] * n
+        # moveref: flow 8 + record read and write + pixmap 3 + frame 3; the records are 4 B packed (13/13/1/5 bits)
+        # up to 8192 x 8192, the reference's int32 x 4 (16 B) beyond
+        packed = max(cfg["height"], cfg["width"]) <= 8192
+        comp += {"moveref": 22.0 if packed else 46.0, "sum": 30.0, "static": 6.0}[kind] * n
         if layer.get("reset_mask"):
             comp += 4.0 * n
     return flow + post + comp

@@ -723,6 +723,43 @@ def test_moveref_fast_path_equals_generic_kernel(reset, rgba_pixmap, tmp_path):
         assert 0.05 < frac < 0.9          # some pixels were reset, not all
 
 
+@pytest.mark.parametrize("shape", [(270, 484), (8200, 8)])
+def test_moveref_packed_records_equal_int32_records(shape, tmp_path, monkeypatch):
+    """The fast kernel keeps the records packed in 32 bits (13/13/1/5) when the frame fits 8192 x 8192; the int32 x 4
+    array is materialised on demand.  Same state and frames as a layer created with packing off, across a state
+    save / restore in the middle (the restored layer re-packs from the int32 array); a frame taller than 8192
+    rows never packs."""
+    import pickle
+    from transflow_b200.compositor import Compositor
+    from transflow_b200.compositor.pixmap_source_interface import PixmapSourceInterface, StillQueue
+    from transflow_b200.config import LayerConfig
+    h, w = shape
+    rng = np.random.default_rng(5)
+    pix = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+
+    def make():
+        c = Compositor.from_args(h, w, [LayerConfig(0, "moveref", reset_mode="random", reset_random_factor=0.3)],
+                                 background_color="#102030", seed=9)
+        c.set_sources({0: [PixmapSourceInterface(StillQueue(dev(pix)), np.ones((h, w), bool))]})
+        return c
+    packed = make()
+    monkeypatch.setenv("TFB200_PACKED_RECORDS", "0")
+    plain = make()
+    monkeypatch.delenv("TFB200_PACKED_RECORDS")
+    for t in range(6):
+        flow = F.post_process(rng.uniform(-3, 3, (h, w, 2)).astype(np.float32), False)
+        flow[rng.random((h, w)) < 0.3] = 0
+        a, b = packed.step(flow).cpu().numpy(), plain.step(flow).cpu().numpy()
+        np.testing.assert_array_equal(a, b, err_msg=f"frame {t}")
+        if t == 2:
+            state = pickle.loads(pickle.dumps(packed.layers[0].__getstate__()))
+            np.testing.assert_array_equal(state["data"], plain.layers[0].data)
+            packed.layers[0].__setstate__(state)
+        if t in (3, 5):
+            np.testing.assert_array_equal(packed.layers[0].data, plain.layers[0].data, err_msg=f"data {t}")
+            np.testing.assert_array_equal(packed.layers[0].rgba, plain.layers[0].rgba, err_msg=f"rgba {t}")
+
+
 # ------------------------------------------------------------------------------------------------
 # flow visualisers (output/render.py:9-48), bit-exact against frames the reference rendered
 # ------------------------------------------------------------------------------------------------

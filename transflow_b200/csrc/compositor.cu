@@ -15,6 +15,12 @@ struct tf_layer {
     int h, w, depth;
     int4* data[2];   // ping-pong (the move is a gather from the previous state)
     int cur;
+    // moveref layers also keep the records PACKED in 32 bits (i: 13, j: 13, alpha: 1, source: 5 -- frames up to
+    // 8192 x 8192, 32 sources): the fast kernel gathers and writes 4 bytes per pixel instead of 16.  The int32 x 4
+    // array of the reference (`layer.data`) is materialised from it on demand, and the other way round.
+    uint32_t* pdata[2];
+    int pcur;
+    bool packed_ok, int4_valid, packed_valid;
     uchar4* rgba;    // persistent Layer.rgba (reference / static layers)
     uint8_t* mask_src;
     uint8_t* mask_dst;
@@ -346,6 +352,8 @@ struct FastParams {
     const float2* flow;
     const int4* old;
     int4* out;
+    const uint32_t* oldp;   // packed records (PACKED kernels)
+    uint32_t* outp;
     uchar4* rgba;
     const float* reset_scale;
     float reset_factor;
@@ -359,7 +367,29 @@ struct FastParams {
 
 // SUM: the same kernel for the `sum` layer (sum.py:9-10) -- no gather, the record of the pixel itself moves by
 // floor(flow) (x to the ROW index, quirk Q8), in place (old == out); the reset, remap and composite stages are shared.
-template <int RESET, int CHAN, bool SUM = false>
+__device__ __forceinline__ int4 rec_unpack(uint32_t r) {
+    return make_int4((int)(r & 0x1FFFu), (int)((r >> 13) & 0x1FFFu), (int)((r >> 26) & 1u), (int)(r >> 27));
+}
+__device__ __forceinline__ uint32_t rec_pack(int4 r) {
+    return ((uint32_t)r.x & 0x1FFFu) | (((uint32_t)r.y & 0x1FFFu) << 13) | ((r.z != 0 ? 1u : 0u) << 26) |
+           (((uint32_t)r.w & 31u) << 27);
+}
+// int32 x 4 records <-> packed records; a record that does not fit sets bit 1 of the layer's error word
+__global__ void __launch_bounds__(256) k_pack_records(const int4* __restrict__ src, uint32_t* __restrict__ dst, int n,
+                                                      int* __restrict__ err) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int4 r = src[p];
+    if ((unsigned)r.x > 8191u || (unsigned)r.y > 8191u || (unsigned)r.z > 1u || (unsigned)r.w > 31u) atomicOr(err, 2);
+    dst[p] = rec_pack(r);
+}
+__global__ void __launch_bounds__(256) k_unpack_records(const uint32_t* __restrict__ src, int4* __restrict__ dst, int n) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    dst[p] = rec_unpack(src[p]);
+}
+
+template <int RESET, int CHAN, bool SUM = false, bool PACKED = false>
 __global__ void __launch_bounds__(256) k_moveref_fast(FastParams P) {
     const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (p0 >= P.n) return;
@@ -388,11 +418,11 @@ __global__ void __launch_bounds__(256) k_moveref_fast(FastParams P) {
             q[k] = moved[k] ? wrap_index(p0 + k + off, P.n, p0 + k, P.err) : p0 + k;
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++) rec[k] = __ldg(P.old + q[k]);
+        for (int k = 0; k < 4; k++) rec[k] = PACKED ? rec_unpack(__ldg(P.oldp + q[k])) : __ldg(P.old + q[k]);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             // a transparent source does not move (movement.py:34-35): keep the pixel's own record
-            if (moved[k] && rec[k].z == 0) rec[k] = __ldg(P.old + p0 + k);
+            if (moved[k] && rec[k].z == 0) rec[k] = PACKED ? rec_unpack(__ldg(P.oldp + p0 + k)) : __ldg(P.old + p0 + k);
             else if (moved[k]) rec[k].z = 1;
         }
     }
@@ -439,8 +469,12 @@ __global__ void __launch_bounds__(256) k_moveref_fast(FastParams P) {
             if (CHAN == 3) px[k].w = 0;
         }
     }
+    if (PACKED) {
+        *reinterpret_cast<uint4*>(P.outp + p0) = make_uint4(rec_pack(rec[0]), rec_pack(rec[1]), rec_pack(rec[2]), rec_pack(rec[3]));
+    } else {
 #pragma unroll
-    for (int k = 0; k < 4; k++) P.out[p0 + k] = rec[k];
+        for (int k = 0; k < 4; k++) P.out[p0 + k] = rec[k];
+    }
     *reinterpret_cast<uint4*>(P.rgba + p0) = make_uint4(*reinterpret_cast<uint32_t*>(&px[0]), *reinterpret_cast<uint32_t*>(&px[1]),
                                                         *reinterpret_cast<uint32_t*>(&px[2]), *reinterpret_cast<uint32_t*>(&px[3]));
     // composite over the constant background, 12 packed bytes
@@ -661,6 +695,14 @@ extern "C" int tf_layer_create(tf_layer** out, int height, int width, const tf_l
             if (cudaMalloc(&l->vacated, n * 4) != cudaSuccess) return bail(fail(TF_ERR_CUDA, "cudaMalloc failed"));
             cudaMemset(l->vacated, 0, n * 4);
         }
+        l->int4_valid = true;
+        const char* pk = getenv("TFB200_PACKED_RECORDS");
+        if (cfg->kind == TF_LAYER_MOVEREF && height <= 8192 && width <= 8192 && !(pk && pk[0] == '0')) {
+            for (int i = 0; i < 2; i++)
+                if (cudaMalloc(&l->pdata[i], n * sizeof(uint32_t)) != cudaSuccess)
+                    return bail(fail(TF_ERR_CUDA, "cudaMalloc(packed data) failed for %dx%d", height, width));
+            l->packed_ok = true;
+        }
     }
     if (cfg->kind != TF_LAYER_INTRODUCTION) {
         if (cudaMalloc(&l->rgba, n * 4) != cudaSuccess) return bail(fail(TF_ERR_CUDA, "cudaMalloc(rgba) failed"));
@@ -674,9 +716,28 @@ extern "C" int tf_layer_create(tf_layer** out, int height, int width, const tf_l
     return TF_OK;
 }
 
+// the int32 x 4 array / the packed array is brought up to date from the other one when a consumer needs it
+static int ensure_int4(tf_layer* l, cudaStream_t st) {
+    if (l->int4_valid || !l->data[l->cur]) return TF_OK;
+    int n = l->h * l->w;
+    k_unpack_records<<<ceil_div(n, 256), 256, 0, st>>>(l->pdata[l->pcur], l->data[l->cur], n);
+    TF_LAUNCHED();
+    l->int4_valid = true;
+    return TF_OK;
+}
+static int ensure_packed(tf_layer* l, cudaStream_t st) {
+    if (l->packed_valid) return TF_OK;
+    int n = l->h * l->w;
+    k_pack_records<<<ceil_div(n, 256), 256, 0, st>>>(l->data[l->cur], l->pdata[l->pcur], n, l->err);
+    TF_LAUNCHED();
+    l->packed_valid = true;
+    return TF_OK;
+}
+
 extern "C" int tf_layer_destroy(tf_layer* l) {
     if (!l) return TF_OK;
     cudaFree(l->data[0]); cudaFree(l->data[1]); cudaFree(l->rgba);
+    cudaFree(l->pdata[0]); cudaFree(l->pdata[1]);
     cudaFree(l->mask_src); cudaFree(l->mask_dst); cudaFree(l->mask_alpha); cudaFree(l->reset_scale);
     cudaFree(l->base_src); cudaFree(l->vacated); cudaFree(l->err);
     for (int s = 0; s < TF_MAX_SOURCES; s++) cudaFree(l->intro[s]);
@@ -734,8 +795,10 @@ extern "C" int tf_layer_set_sources(tf_layer* l, int n_sources, const uint8_t* c
         int blocks = ceil_div((int)n, 256);
         k_base_source<<<blocks, 256, 0, st>>>(l->base_src, P);
         TF_LAUNCHED();
+        if (int e = ensure_int4(l, st)) return e;
         k_init_reference_data<<<blocks, 256, 0, st>>>(l->data[l->cur], l->base_src, l->h, l->w, 1);
         TF_LAUNCHED();
+        l->packed_valid = false;
     }
     return TF_OK;
 }
@@ -782,6 +845,7 @@ extern "C" int tf_layer_update(tf_layer* l, const float* flow, const tf_pixmap* 
         bool leave = kind != TF_LAYER_SUM && l->cfg.moving_pixels_leave_empty_spot;
         if (kind == TF_LAYER_MOVEREF) {
             if (leave) {
+                if (int e = ensure_int4(l, st)) return e;
                 k_mark_vacated<0><<<blocks1, 256, 0, st>>>(P, 1);
                 TF_LAUNCHED();
             }
@@ -791,15 +855,30 @@ extern "C" int tf_layer_update(tf_layer* l, const float* flow, const tf_pixmap* 
                         (c.reset_mode == TF_RESET_OFF || (c.reset_mode == TF_RESET_RANDOM && !random && !c.reset_source)) &&
                         rgb_inout && first_layer && (P.n & 3) == 0 && ((uintptr_t)flow & 15) == 0 &&
                         ((uintptr_t)l->reset_scale & 15) == 0;
+            const bool packed = fast && l->packed_ok;
+            if (packed) {
+                if (int e = ensure_packed(l, st)) return e;
+            } else {
+                if (int e = ensure_int4(l, st)) return e;
+            }
             {
                 ScopedKernelTimer timer(TFK_COMPOSITOR_LAYER, st);
                 if (fast) {
                     FastParams F;
                     F.flow = P.flow; F.old = P.old; F.out = P.out; F.rgba = P.rgba; F.reset_scale = l->reset_scale;
+                    F.oldp = l->pdata[l->pcur]; F.outp = l->pdata[l->pcur ^ 1];
                     F.reset_factor = c.reset_random_factor; F.pix = P.pix[0]; F.rgb = rgb_inout; F.bg = background_rgb;
                     F.h = P.h; F.w = P.w; F.n = P.n; F.seed = P.seed; F.frame = P.frame; F.err = P.err;
                     bool rnd = c.reset_mode == TF_RESET_RANDOM;
-                    if (P.chan[0] == 4) {
+                    if (packed) {
+                        if (P.chan[0] == 4) {
+                            if (rnd) k_moveref_fast<TF_RESET_RANDOM, 4, false, true><<<blocks4, 256, 0, st>>>(F);
+                            else k_moveref_fast<TF_RESET_OFF, 4, false, true><<<blocks4, 256, 0, st>>>(F);
+                        } else {
+                            if (rnd) k_moveref_fast<TF_RESET_RANDOM, 3, false, true><<<blocks4, 256, 0, st>>>(F);
+                            else k_moveref_fast<TF_RESET_OFF, 3, false, true><<<blocks4, 256, 0, st>>>(F);
+                        }
+                    } else if (P.chan[0] == 4) {
                         if (rnd) k_moveref_fast<TF_RESET_RANDOM, 4><<<blocks4, 256, 0, st>>>(F);
                         else k_moveref_fast<TF_RESET_OFF, 4><<<blocks4, 256, 0, st>>>(F);
                     } else {
@@ -811,7 +890,13 @@ extern "C" int tf_layer_update(tf_layer* l, const float* flow, const tf_pixmap* 
                 }
             }
             TF_LAUNCHED();
-            l->cur ^= 1;
+            if (packed) {
+                l->pcur ^= 1;
+                l->int4_valid = false;
+            } else {
+                l->cur ^= 1;
+                l->packed_valid = false;
+            }
         } else if (kind == TF_LAYER_SUM) {
             const tf_layer_config& c = l->cfg;
             // single source, no alpha mask, reset off or random with device draws, fused single layer: the fast kernel
@@ -896,8 +981,10 @@ extern "C" int tf_layer_get_state(tf_layer* l, int32_t* data, uint8_t* rgba, voi
     TF_REQUIRE(l, TF_ERR_INVALID_ARG, "tf_layer_get_state: null layer");
     size_t n = (size_t)l->h * l->w;
     cudaStream_t st = as_stream(stream);
-    if (data && l->data[l->cur])
+    if (data && l->data[l->cur]) {
+        if (int e = ensure_int4(l, st)) return e;
         TF_CUDA(cudaMemcpyAsync(data, l->data[l->cur], n * l->depth * 4, cudaMemcpyDeviceToDevice, st));
+    }
     if (rgba && l->rgba) TF_CUDA(cudaMemcpyAsync(rgba, l->rgba, n * 4, cudaMemcpyDeviceToDevice, st));
     return TF_OK;
 }
@@ -906,8 +993,11 @@ extern "C" int tf_layer_set_state(tf_layer* l, const int32_t* data, const uint8_
     TF_REQUIRE(l, TF_ERR_INVALID_ARG, "tf_layer_set_state: null layer");
     size_t n = (size_t)l->h * l->w;
     cudaStream_t st = as_stream(stream);
-    if (data && l->data[l->cur])
+    if (data && l->data[l->cur]) {
         TF_CUDA(cudaMemcpyAsync(l->data[l->cur], data, n * l->depth * 4, cudaMemcpyDeviceToDevice, st));
+        l->int4_valid = true;
+        l->packed_valid = false;
+    }
     if (rgba && l->rgba) TF_CUDA(cudaMemcpyAsync(l->rgba, rgba, n * 4, cudaMemcpyDeviceToDevice, st));
     return TF_OK;
 }
@@ -917,6 +1007,7 @@ extern "C" int tf_layer_poll_error(tf_layer* l, void* stream) {
     int v = 0;
     TF_CUDA(cudaMemcpyAsync(&v, l->err, sizeof(int), cudaMemcpyDeviceToHost, as_stream(stream)));
     TF_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    if (v & 2) return fail(TF_ERR_CUDA, "internal: a layer record does not fit the packed 13/13/1/5-bit form");
     if (v) return fail(TF_ERR_INDEX, "index out of bounds: a flow vector points outside the frame "
                                      "(post-process the flow or clip it first)");
     return TF_OK;
