@@ -89,7 +89,10 @@ TF_API int tf_farneback_prepare(tf_farneback* h, int slot, const uint8_t* gray, 
  * rolling-tile kernel (fb_tile.cuh) on the smaller ones; 4-7 = half-buffer kernel everywhere (scalar or 128-bit
  * shared accesses, 4 or 3 CTAs per SM); 3 = rolling-tile kernel everywhere; 1 = unfused reference kernels
  * (M and double vertical sums materialised in HBM); 0 / 2 = fused column-streaming kernel with
- * float / double sums in shared memory (kept for comparison).
+ * float / double sums in shared memory (kept for comparison); 17-24 = configurations of the half-buffer kernel and
+ * the TMA-fed ring kernels (fb_ring.cuh); 25 = packed half-buffer kernel (channel pairs in shared memory, FADD2 window
+ * sums, fb_pack.cuh), 27 = the same with pairs of rows sharing their middle tap row -- both bit-identical to 8;
+ * 28 / 29 = timing experiments (phase A only / phases B + C only of variant 25: NOT a flow), winsize 15 only.
  * If clip != 0 the final clip of FlowSource.post_process (source.py:361-362) is fused into
  * the last store. */
 TF_API int tf_farneback_solve(tf_farneback* h, int slot_left, int slot_right, float* flow, int variant,
@@ -129,7 +132,8 @@ TF_API int tf_farneback_debug_read(tf_farneback* h, int slot, int level_index, i
                             void* stream);
 /* Tuning knob for experiments (process-wide): key 0 = rows per CTA of the variant 4-7 kernels (0 = heuristic);
  * key 1 = 1 selects the separate horizontal / vertical pyramid blur passes instead of the fused kernel;
- * key 2 = smallest level (pixels) the key-0 override applies to. */
+ * key 2 = smallest level (pixels) the key-0 override applies to; key 3 / 4 = rows per CTA / smallest level of the ring
+ * kernels. */
 TF_API int tf_farneback_tune(int key, int value);
 /* Algorithmic bytes moved per solved pair (SURVEY.md 8d model), for roofline reporting. */
 TF_API double tf_farneback_algorithmic_bytes(const tf_farneback* h, int reuse_r);

@@ -298,9 +298,10 @@ def test_farneback_edge_sizes(shape, variant):
     assert mean <= 1e-3 and mx <= 2e-2, (mean, mx)
 
 
-@pytest.mark.parametrize("variant", [9, 10, 11, 12, 13, 14, 15, 16, 18, 19, 20, 21, 22, 23, 24])
+@pytest.mark.parametrize("variant", [9, 10, 11, 12, 13, 14, 15, 16, 18, 19, 20, 21, 22, 23, 24, 25, 27])
 def test_farneback_staged_kernel_is_bit_identical_to_default(variant):
-    """Variants 9 / 10 (R1 box staged in shared memory by bulk copies + mbarrier, global fallback outside the box; 64-
+    """Variants 25 / 27: the packed half-buffer kernel (channel pairs in shared memory, FADD2 window sums; 27 shares the
+    middle tap row of a pair of rows).  Variants 9 / 10 (R1 box staged in shared memory by bulk copies + mbarrier, global fallback outside the box; 64-
     or 32-column strips) run the same arithmetic as the default kernel: identical flows, also when the motion
     exceeds the staging margin."""
     from transflow_b200 import ops
@@ -327,7 +328,7 @@ def test_ring_and_default_kernels_ragged_sizes(shape):
         want = ops.Farneback(h, w, variant=8)(dev(g0), dev(right))
         mean, mx = epe(want.cpu().numpy(), F.farneback(g0, right))
         assert mean <= 0.01 and mx <= 0.1, (mean, mx)
-        for variant in (19, 21, 23):
+        for variant in (19, 21, 23, 25, 27):
             fb = ops.Farneback(h, w, variant=variant)
             for rep in range(3):
                 assert torch.equal(fb(dev(g0), dev(right)), want), (variant, rep)
