@@ -425,6 +425,8 @@ def run_reference(args):
 
 def cpu_baseline_sample(cfg):
     """The reference CPU path timed on this box's host cores on a bounded sample (about 10-30 s of CPU work)."""
+    if os.environ.get("TFB200_BENCH_SKIP_CPU") == "1":      # kernel A/B runs only; the contract's line always has it
+        return None
     n = 2
     hs = _band_rows(cfg, 6.0)
     with tempfile.TemporaryDirectory() as tmp:
@@ -601,8 +603,11 @@ def run_ours(args):
                 ev_ready[k].record(flow_streams[lane])
         if pipelined:
             main.wait_event(ev_ready[k])
-        post(flows[k])
-        comp.step(flows[k], rgb)
+        if forward:
+            comp.step(post.claims(flows[k]), rgb)      # scatter pass -> claim plane -> compositor (no gather pass)
+        else:
+            post(flows[k])
+            comp.step(flows[k], rgb)
         if pipelined:
             ev_free[k].record(main)
             if serial:      # kernel-alone pass: nothing of frame t+1 may overlap frame t
@@ -759,7 +764,7 @@ def run_e2e(args, cfg, clip, pixmaps, mask_png):
     checksum = 0
     p = cv_params(cfg)
     with FlowSource.from_args(cap, cv_config=CvFlowConfig(**p), direction=cfg["direction"]) as src:
-        src.output = "device"
+        src.output = "claims"       # device flows; forward flows reach Compositor.step as the scatter's claim plane
         t0 = dt = None
         for i, flow in enumerate(src):
             if i == n_warm:

@@ -185,6 +185,14 @@ typedef struct tf_flow_op {
  * ops is a HOST array (copied into the launch).  out == NULL -> in place. */
 TF_API int tf_flow_postprocess_ex(float* flow, const tf_flow_op* ops, int n_ops, const float* mask, int forward,
                                   int32_t* owner, float* out, int height, int width, void* stream);
+/* The forward direction's two passes on their own (source.py:349-360).  tf_flow_forward_claims: filters + mask + clip +
+ * round half-even, then every moved pixel p claims its target with max(p + 1) into `claims` (int32 (H, W), all zero on
+ * entry: numpy.put keeps the LAST source in raster order).  tf_flow_from_claims turns the claims into the flow the
+ * reference returns (claimant - own position, 0 where unclaimed) and zeroes them again.  tf_layer_update_claims consumes
+ * the claim plane directly, so a pipeline whose only consumer is the compositor never forms that flow. */
+TF_API int tf_flow_forward_claims(const float* flow, const tf_flow_op* ops, int n_ops, const float* mask,
+                                  int32_t* claims, int height, int width, void* stream);
+TF_API int tf_flow_from_claims(int32_t* claims, float* flow_out, int height, int width, void* stream);
 /* filters + mask only -> out (the stage in front of the convolution kernel). */
 TF_API int tf_flow_filters(const float* flow, const tf_flow_op* ops, int n_ops, const float* mask, float* out,
                            int height, int width, void* stream);
@@ -264,6 +272,13 @@ TF_API int tf_layer_set_sources(tf_layer* l, int n_sources, const uint8_t* const
 TF_API int tf_layer_update(tf_layer* l, const float* flow, const tf_pixmap* pixmaps_host, int n_pixmaps,
                     const double* random, uint64_t rng_seed, uint8_t* rgb_inout, int first_layer,
                     uint32_t background_rgb, void* stream);
+/* Layer.update for a FORWARD flow given as the claim plane of tf_flow_forward_claims (consumed and zeroed): the record a
+ * pixel fetches is its claimant's (movement.py:25-50 with flow = claimant - position), bit-identical to tf_layer_update
+ * on the flow of tf_flow_from_claims.  Only for layers tf_layer_takes_claims() accepts (returns 1): a single-source
+ * move-reference layer in its default movement configuration, rendered fused as the first layer; others take the flow. */
+TF_API int tf_layer_takes_claims(const tf_layer* l, int n_pixmaps);
+TF_API int tf_layer_update_claims(tf_layer* l, int32_t* claims, const tf_pixmap* pixmaps_host, int n_pixmaps,
+                                  uint64_t rng_seed, uint8_t* rgb_inout, uint32_t background_rgb, void* stream);
 /* Layer.render (compositor/layers/layer.py:32-34): alpha *= mask_alpha in place; -> uint8 rgba. */
 TF_API int tf_layer_render(tf_layer* l, uint8_t* rgba_out, void* stream);
 /* Compositor.render (compositor/compositor.py:31-40) over n rendered layers (device rgba). */

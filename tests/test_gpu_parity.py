@@ -724,6 +724,71 @@ def test_moveref_fast_path_equals_generic_kernel(reset, rgba_pixmap, tmp_path):
         assert 0.05 < frac < 0.9          # some pixels were reset, not all
 
 
+@pytest.mark.parametrize("rgba_pixmap", [False, True])
+@pytest.mark.parametrize("reset", ["off", "random"])
+def test_forward_claims_equal_the_postprocessed_flow(reset, rgba_pixmap, tmp_path):
+    """Forward direction: the scatter pass's claim plane fed straight to the move-reference layer
+    (PostProcess.claims -> Compositor.step, tf_layer_update_claims) gives the same frames and the same layer state as the
+    two-pass post-process followed by the flow-fed update, which the golden cases pin to the reference; the tensor a
+    claims object forms on demand is the post-processed flow itself; a multi-layer compositor falls back to the flow."""
+    from transflow_b200 import ops
+    from transflow_b200.compositor import Compositor
+    from transflow_b200.compositor.pixmap_source_interface import PixmapSourceInterface, StillQueue
+    from transflow_b200.config import LayerConfig
+    from transflow_b200.synthetic import radial_mask
+    import PIL.Image
+    h, w = 270, 484
+    rng = np.random.default_rng(33)
+    pix = rng.integers(0, 256, (h, w, 4 if rgba_pixmap else 3), dtype=np.uint8)
+    if rgba_pixmap:
+        pix[..., 3] = np.where(rng.random((h, w)) < 0.3, 0, pix[..., 3])
+    mask_png = str(tmp_path / "m.png")
+    PIL.Image.fromarray(np.rint(radial_mask(h, w) * 255).astype(np.uint8)).save(mask_png)
+    kw = dict(reset_mode=reset, reset_random_factor=0.5, reset_mask=mask_png if reset == "random" else None)
+    comps = []
+    for _ in range(2):
+        c = Compositor.from_args(h, w, [LayerConfig(0, "moveref", **kw)], background_color="#123456", seed=5)
+        c.set_sources({0: [PixmapSourceInterface(StillQueue(dev(pix)), np.ones((h, w), bool))]})
+        comps.append(c)
+    assert comps[1].layers[0].takes_claims()
+    fmask = dev(rng.random((h, w)).astype(np.float32))
+    for mask in (None, fmask):
+        post_a, post_b = (ops.PostProcess(h, w, forward=True, mask=mask) for _ in range(2))
+        for t in range(4):
+            raw = rng.uniform(-6, 6, (h, w, 2)).astype(np.float32)
+            raw[rng.random((h, w)) < 0.2] = 0
+            filt = [("scale", 1.5)] if t & 1 else None
+            want_flow = post_a(dev(raw), ops=filt)
+            claims = post_b.claims(dev(raw), ops=filt)
+            if t == 2:      # any other consumer: the tensor is the post-processed flow, and the compositor then takes that
+                assert torch.equal(claims.tensor(), want_flow)
+                assert not claims.live
+            a = comps[0].step(want_flow).cpu().numpy()
+            b = comps[1].step(claims).cpu().numpy()
+            np.testing.assert_array_equal(a, b, err_msg=f"frame {t}")
+            np.testing.assert_array_equal(comps[0].layers[0].data, comps[1].layers[0].data, err_msg=f"data {t}")
+            np.testing.assert_array_equal(comps[0].layers[0].rgba, comps[1].layers[0].rgba, err_msg=f"rgba {t}")
+            if t != 2:
+                assert not claims.live
+                with pytest.raises(RuntimeError):
+                    claims.tensor()
+        assert int(post_b._claim_ring[0][0].abs().sum()) == 0       # consumed planes are left all zero
+    # recycled before use: the plane is cleared and the stale object says so
+    post = ops.PostProcess(h, w, forward=True)
+    raw = dev(rng.uniform(-3, 3, (h, w, 2)).astype(np.float32))
+    first = post.claims(raw)
+    others = [post.claims(raw) for _ in range(ops.PostProcess.CLAIM_PLANES)]
+    assert not first.live and others[-1].live
+    assert torch.equal(others[-1].tensor(), ops.PostProcess(h, w, forward=True)(raw.clone()))
+    # two layers: the flow is formed once and both layers take it
+    two = Compositor.from_args(h, w, [LayerConfig(0, "moveref"), LayerConfig(1, "moveref")], background_color="#000000")
+    two.set_sources({i: [PixmapSourceInterface(StillQueue(dev(pix)), np.ones((h, w), bool))] for i in range(2)})
+    ref = Compositor.from_args(h, w, [LayerConfig(0, "moveref"), LayerConfig(1, "moveref")], background_color="#000000")
+    ref.set_sources({i: [PixmapSourceInterface(StillQueue(dev(pix)), np.ones((h, w), bool))] for i in range(2)})
+    np.testing.assert_array_equal(two.step(post.claims(raw)).cpu().numpy(),
+                                  ref.step(ops.PostProcess(h, w, forward=True)(raw.clone())).cpu().numpy())
+
+
 @pytest.mark.parametrize("shape", [(270, 484), (8200, 8)])
 def test_moveref_packed_records_equal_int32_records(shape, tmp_path, monkeypatch):
     """The fast kernel keeps the records packed in 32 bits (13/13/1/5) when the frame fits 8192 x 8192; the int32 x 4

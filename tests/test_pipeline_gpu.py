@@ -113,6 +113,36 @@ def test_checkpoint_file_round_trip(tmp_path, layer_kw):
     assert meta["cursor"] == ckpt and meta["framerate"] == fps and meta["config"]["flow_path"] == str(avi)
 
 
+@pytest.mark.parametrize("layer_kw", [dict(), dict(reset_mode="random", reset_random_factor=0.5)])
+def test_pipeline_forward_claims_equal_flow_path(tmp_path, monkeypatch, layer_kw):
+    """A forward pipeline whose only flow consumer is a single move-reference layer hands the scatter pass's claim plane
+    to the compositor (``flow_source.output == "claims"``); the frames equal those of the flow-fed path bit for bit, and
+    a pipeline with a flow visualiser keeps the flow."""
+    import PIL.Image
+    from transflow_b200.config import LayerConfig, PixmapSourceConfig
+    from transflow_b200.pipeline import Config
+    from transflow_b200.synthetic import synthetic_clip
+    h, w, n = 72, 96, 6
+    avi = tmp_path / "flow.avi"
+    write_avi(avi, synthetic_clip(h, w, n + 2, seed=9), 25)
+    frames = {}
+    for tag, env in (("claims", "1"), ("flow", "0")):
+        monkeypatch.setenv("TFB200_FORWARD_CLAIMS", env)
+        cfg = Config(str(avi), pixmap_sources=[PixmapSourceConfig("cnoise", layers=[0])],
+                     layers=[LayerConfig(0, "moveref", **layer_kw)], output_path=str(tmp_path / (tag + "-%d.png")),
+                     direction="forward", duration_time=n / 25, seed=3)
+        pipe = _run_pipeline(cfg)
+        assert pipe.flow_source.output == ("claims" if env == "1" else "device")
+        frames[tag] = [np.asarray(PIL.Image.open(tmp_path / f"{tag}-{i}.png")) for i in range(n)]
+    for i in range(n):
+        assert np.array_equal(frames["claims"][i], frames["flow"][i]), i
+    assert any(not np.array_equal(frames["claims"][0], f) for f in frames["claims"][1:])   # the frames do change
+    monkeypatch.setenv("TFB200_FORWARD_CLAIMS", "1")
+    cfg = Config(str(avi), pixmap_sources=[PixmapSourceConfig("cnoise", layers=[0])], layers=[LayerConfig(0, "moveref")],
+                 output_path=str(tmp_path / "v-%d.png"), direction="forward", duration_time=2 / 25, view_flow=True)
+    assert _run_pipeline(cfg).flow_source.output == "device"
+
+
 def test_layer_masks_and_seed_survive_pickle():
     """A ``random`` mask is redrawn from its config string on construction; the pickled layer must carry the array
     (the reference pickles its mask arrays).  Two layers of one compositor draw different reset numbers."""

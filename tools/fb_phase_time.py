@@ -13,7 +13,7 @@ h, w = 2160, 3840
 clip = synthetic_clip(h, w, 2, seed=1)
 a, b = (torch.from_numpy(F.gray_from_bgr(f)).cuda() for f in clip)
 out = torch.empty((h, w, 2), dtype=torch.float32, device="cuda")
-for v in (24, 25, 28, 29, 25, 28, 29):
+for v in (24, 25, 28, 29, 30, 25, 28, 29, 30):
     fb = ops.Farneback(h, w, variant=v)
     fb.prepare(0, a); fb.prepare(1, b)
     for _ in range(3): fb.solve(0, 1, out)

@@ -95,6 +95,8 @@ SIGNATURES = {
     "tf_flow_postprocess": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp]),
     "tf_flow_postprocess_to": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "tf_flow_postprocess_ex": (_i, [_vp, C.POINTER(FlowOpStruct), _i, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "tf_flow_forward_claims": (_i, [_vp, C.POINTER(FlowOpStruct), _i, _vp, _vp, _i, _i, _vp]),
+    "tf_flow_from_claims": (_i, [_vp, _vp, _i, _i, _vp]),
     "tf_flow_filters": (_i, [_vp, C.POINTER(FlowOpStruct), _i, _vp, _vp, _i, _i, _vp]),
     "tf_flow_convolve": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "tf_flow_merge": (_i, [C.POINTER(_vp), _i, _i, _vp, _i, _i, _vp]),
@@ -107,6 +109,8 @@ SIGNATURES = {
     "tf_layer_set_masks": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "tf_layer_set_sources": (_i, [_vp, _i, C.POINTER(_vp), _vp]),
     "tf_layer_update": (_i, [_vp, _vp, C.POINTER(PixmapStruct), _i, _vp, _u64, _vp, _i, _u32, _vp]),
+    "tf_layer_takes_claims": (_i, [_vp, _i]),
+    "tf_layer_update_claims": (_i, [_vp, _vp, C.POINTER(PixmapStruct), _i, _u64, _vp, _u32, _vp]),
     "tf_layer_render": (_i, [_vp, _vp, _vp]),
     "tf_composite": (_i, [C.POINTER(_vp), _i, _u32, _vp, _i, _i, _vp]),
     "tf_layer_depth": (_i, [_vp]),

@@ -41,6 +41,8 @@ class Compositor:
         return (int(r) << 16) | (int(g) << 8) | int(b)
 
     def update(self, flow):
+        if hasattr(flow, "take") and hasattr(flow, "tensor"):
+            flow = flow.tensor()
         for layer in self.layers:
             layer.update(flow)
 
@@ -66,6 +68,12 @@ class Compositor:
         if not self.layers:
             out[:, :] = torch.tensor(self.background_color, dtype=torch.uint8, device="cuda")
             return out
+        if hasattr(flow, "take") and hasattr(flow, "tensor"):
+            # ops.ForwardClaims: a single move-reference layer reads the claim plane itself (no flow in HBM at all)
+            if len(self.layers) == 1 and flow.live and self.layers[0].takes_claims():
+                self.layers[0]._update_claims(flow, out, background=self._bg_word)
+                return out
+            flow = flow.tensor()
         for i, layer in enumerate(self.layers):
             layer._update(flow, rgb_inout=out, first_layer=(i == 0), background=self._bg_word)
         return out

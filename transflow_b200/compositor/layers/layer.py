@@ -159,7 +159,29 @@ class Layer:
     def _needs_pixmaps(self) -> bool:
         return True
 
+    def takes_claims(self) -> bool:
+        """Can ``Compositor.step`` feed this layer a forward flow as ``ops.ForwardClaims`` (the scatter pass's claim
+        plane) instead of the flow?  Single-source move-reference layers on the fast kernel, device-side reset draws."""
+        return (self.KIND == "moveref" and self.reset_rng != "numpy" and
+                bool(self._lib.tf_layer_takes_claims(self._handle, len(self.sources))))
+
+    def _update_claims(self, claims, rgb_inout, background=0):
+        pixmaps = self._pull_pixmaps()
+        arr = (PixmapStruct * 1)()
+        pm = pixmaps[0]
+        if tuple(pm.shape[:2]) != (self.height, self.width):
+            raise ValueError(f"pixmap must be ({self.height}, {self.width}, C), got {tuple(pm.shape)}")
+        arr[0].pixels = pm.data_ptr()
+        arr[0].channels = int(pm.shape[2])
+        arr[0].frame_number = int(self.sources[0].frame_number)
+        plane = claims.take()
+        check(self._lib.tf_layer_update_claims(self._handle, ptr(plane), arr, 1, self.rng_seed, ptr(rgb_inout),
+                                               int(background), stream_ptr()))
+        self._keepalive = (plane, pixmaps, None)
+
     def _update(self, flow, rgb_inout=None, first_layer=False, background=0):
+        if hasattr(flow, "take") and hasattr(flow, "tensor"):       # ops.ForwardClaims outside Compositor.step
+            flow = flow.tensor()
         fl = None if self.KIND == "static" else flow_to_device(flow)
         if fl is not None and tuple(fl.shape) != (self.height, self.width, 2):
             raise ValueError(f"flow must be ({self.height}, {self.width}, 2), got {tuple(fl.shape)}")

@@ -350,6 +350,7 @@ __global__ void __launch_bounds__(256) k_reference_layer(LayerParams P) {
 // thread's four pixels move as 128-bit words end to end.
 struct FastParams {
     const float2* flow;
+    int* owner;             // OWNER kernels: the forward scatter's claim plane instead of the flow (consumed and re-zeroed)
     const int4* old;
     int4* out;
     const uint32_t* oldp;   // packed records (PACKED kernels)
@@ -389,12 +390,20 @@ __global__ void __launch_bounds__(256) k_unpack_records(const uint32_t* __restri
     dst[p] = rec_unpack(src[p]);
 }
 
-template <int RESET, int CHAN, bool SUM = false, bool PACKED = false>
+// OWNER: the flow of the forward direction is "position of the pixel that claimed me - my position" (core.cu,
+// k_post_forward_gather), so the record to fetch is the claimant's: the kernel reads the claim plane of the scatter pass
+// (4 bytes per pixel) directly, the flow is never written or read, and the claims are cleared for the next frame here.
+template <int RESET, int CHAN, bool SUM = false, bool PACKED = false, bool OWNER = false>
 __global__ void __launch_bounds__(256) k_moveref_fast(FastParams P) {
     const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (p0 >= P.n) return;
     float2 f[4];
-    {
+    int own[4];
+    if (OWNER) {
+        int4 o = *reinterpret_cast<const int4*>(P.owner + p0);
+        own[0] = o.x; own[1] = o.y; own[2] = o.z; own[3] = o.w;
+        if ((o.x | o.y | o.z | o.w) != 0) *reinterpret_cast<int4*>(P.owner + p0) = make_int4(0, 0, 0, 0);
+    } else {
         float4 a = __ldg(reinterpret_cast<const float4*>(P.flow + p0));
         float4 b = __ldg(reinterpret_cast<const float4*>(P.flow + p0) + 1);
         f[0] = make_float2(a.x, a.y); f[1] = make_float2(a.z, a.w);
@@ -413,9 +422,14 @@ __global__ void __launch_bounds__(256) k_moveref_fast(FastParams P) {
         bool moved[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            int off = __float2int_rn(f[k].y) * P.w + __float2int_rn(f[k].x);
-            moved[k] = off != 0;
-            q[k] = moved[k] ? wrap_index(p0 + k + off, P.n, p0 + k, P.err) : p0 + k;
+            if (OWNER) {
+                moved[k] = own[k] != 0 && own[k] - 1 != p0 + k;   // a claim by the pixel itself is a zero flow
+                q[k] = moved[k] ? own[k] - 1 : p0 + k;
+            } else {
+                int off = __float2int_rn(f[k].y) * P.w + __float2int_rn(f[k].x);
+                moved[k] = off != 0;
+                q[k] = moved[k] ? wrap_index(p0 + k + off, P.n, p0 + k, P.err) : p0 + k;
+            }
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) rec[k] = PACKED ? rec_unpack(__ldg(P.oldp + q[k])) : __ldg(P.old + q[k]);
@@ -803,11 +817,31 @@ extern "C" int tf_layer_set_sources(tf_layer* l, int n_sources, const uint8_t* c
     return TF_OK;
 }
 
-extern "C" int tf_layer_update(tf_layer* l, const float* flow, const tf_pixmap* pixmaps, int n_pixmaps,
-                               const double* random, uint64_t rng_seed, uint8_t* rgb_inout, int first_layer,
-                               uint32_t background_rgb, void* stream) {
+// does the single-source move-reference layer run on the fast kernel with packed records?  (shared by tf_layer_update
+// and tf_layer_takes_claims; `aligned` = the caller's per-call pointers are 16-byte aligned)
+static bool moveref_fast_ok(const tf_layer* l, int n_pixmaps, bool random_given, bool fused_first, bool aligned) {
+    const tf_layer_config& c = l->cfg;
+    const bool leave = c.moving_pixels_leave_empty_spot;
+    const int n = l->h * l->w;
+    return n_pixmaps == 1 && !leave && !c.transparent_pixels_can_move && c.pixels_can_move_to_empty_spot &&
+           c.pixels_can_move_to_filled_spot && !l->mask_src && !l->mask_dst && !l->mask_alpha &&
+           (c.reset_mode == TF_RESET_OFF || (c.reset_mode == TF_RESET_RANDOM && !random_given && !c.reset_source)) &&
+           fused_first && (n & 3) == 0 && aligned && ((uintptr_t)l->reset_scale & 15) == 0;
+}
+
+extern "C" int tf_layer_takes_claims(const tf_layer* l, int n_pixmaps) {
+    if (!l || l->cfg.kind != TF_LAYER_MOVEREF) return 0;
+    return moveref_fast_ok(l, n_pixmaps, false, true, true) && l->packed_ok ? 1 : 0;
+}
+
+static int layer_update(tf_layer* l, const float* flow, int* owner, const tf_pixmap* pixmaps, int n_pixmaps,
+                        const double* random, uint64_t rng_seed, uint8_t* rgb_inout, int first_layer,
+                        uint32_t background_rgb, void* stream) {
     TF_REQUIRE(l, TF_ERR_INVALID_ARG, "tf_layer_update: null layer");
-    TF_REQUIRE(flow || l->cfg.kind == TF_LAYER_STATIC, TF_ERR_INVALID_ARG, "tf_layer_update: null flow");
+    TF_REQUIRE(flow || owner || l->cfg.kind == TF_LAYER_STATIC, TF_ERR_INVALID_ARG, "tf_layer_update: null flow");
+    TF_REQUIRE(!owner || (l->cfg.kind == TF_LAYER_MOVEREF && l->packed_ok &&
+                          moveref_fast_ok(l, n_pixmaps, random != nullptr, rgb_inout && first_layer, ((uintptr_t)owner & 15) == 0)),
+               TF_ERR_INVALID_ARG, "tf_layer_update_claims: this layer configuration needs the flow (see tf_layer_takes_claims)");
     TF_REQUIRE(n_pixmaps == l->n_sources, TF_ERR_INVALID_ARG, "tf_layer_update: %d pixmaps for %d sources", n_pixmaps,
                l->n_sources);
     TF_REQUIRE(n_pixmaps == 0 || pixmaps, TF_ERR_INVALID_ARG, "tf_layer_update: null pixmap array");
@@ -850,11 +884,8 @@ extern "C" int tf_layer_update(tf_layer* l, const float* flow, const tf_pixmap* 
                 TF_LAUNCHED();
             }
             const tf_layer_config& c = l->cfg;
-            bool fast = n_pixmaps == 1 && !leave && !c.transparent_pixels_can_move && c.pixels_can_move_to_empty_spot &&
-                        c.pixels_can_move_to_filled_spot && !l->mask_src && !l->mask_dst && !l->mask_alpha &&
-                        (c.reset_mode == TF_RESET_OFF || (c.reset_mode == TF_RESET_RANDOM && !random && !c.reset_source)) &&
-                        rgb_inout && first_layer && (P.n & 3) == 0 && ((uintptr_t)flow & 15) == 0 &&
-                        ((uintptr_t)l->reset_scale & 15) == 0;
+            bool fast = moveref_fast_ok(l, n_pixmaps, random != nullptr, rgb_inout && first_layer,
+                                        (((uintptr_t)flow | (uintptr_t)owner) & 15) == 0);
             const bool packed = fast && l->packed_ok;
             if (packed) {
                 if (int e = ensure_packed(l, st)) return e;
@@ -870,7 +901,16 @@ extern "C" int tf_layer_update(tf_layer* l, const float* flow, const tf_pixmap* 
                     F.reset_factor = c.reset_random_factor; F.pix = P.pix[0]; F.rgb = rgb_inout; F.bg = background_rgb;
                     F.h = P.h; F.w = P.w; F.n = P.n; F.seed = P.seed; F.frame = P.frame; F.err = P.err;
                     bool rnd = c.reset_mode == TF_RESET_RANDOM;
-                    if (packed) {
+                    F.owner = owner;
+                    if (packed && owner) {
+                        if (P.chan[0] == 4) {
+                            if (rnd) k_moveref_fast<TF_RESET_RANDOM, 4, false, true, true><<<blocks4, 256, 0, st>>>(F);
+                            else k_moveref_fast<TF_RESET_OFF, 4, false, true, true><<<blocks4, 256, 0, st>>>(F);
+                        } else {
+                            if (rnd) k_moveref_fast<TF_RESET_RANDOM, 3, false, true, true><<<blocks4, 256, 0, st>>>(F);
+                            else k_moveref_fast<TF_RESET_OFF, 3, false, true, true><<<blocks4, 256, 0, st>>>(F);
+                        }
+                    } else if (packed) {
                         if (P.chan[0] == 4) {
                             if (rnd) k_moveref_fast<TF_RESET_RANDOM, 4, false, true><<<blocks4, 256, 0, st>>>(F);
                             else k_moveref_fast<TF_RESET_OFF, 4, false, true><<<blocks4, 256, 0, st>>>(F);
@@ -938,6 +978,19 @@ extern "C" int tf_layer_update(tf_layer* l, const float* flow, const tf_pixmap* 
     }
     l->frames++;
     return TF_OK;
+}
+
+extern "C" int tf_layer_update(tf_layer* l, const float* flow, const tf_pixmap* pixmaps, int n_pixmaps,
+                               const double* random, uint64_t rng_seed, uint8_t* rgb_inout, int first_layer,
+                               uint32_t background_rgb, void* stream) {
+    return layer_update(l, flow, nullptr, pixmaps, n_pixmaps, random, rng_seed, rgb_inout, first_layer, background_rgb,
+                        stream);
+}
+
+extern "C" int tf_layer_update_claims(tf_layer* l, int32_t* claims, const tf_pixmap* pixmaps, int n_pixmaps,
+                                      uint64_t rng_seed, uint8_t* rgb_inout, uint32_t background_rgb, void* stream) {
+    TF_REQUIRE(claims, TF_ERR_INVALID_ARG, "tf_layer_update_claims: null claim plane");
+    return layer_update(l, nullptr, claims, pixmaps, n_pixmaps, nullptr, rng_seed, rgb_inout, 1, background_rgb, stream);
 }
 
 extern "C" int tf_layer_render(tf_layer* l, uint8_t* rgba_out, void* stream) {

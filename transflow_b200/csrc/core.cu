@@ -384,6 +384,35 @@ extern "C" int tf_flow_postprocess_ex(float* flow, const tf_flow_op* ops, int n_
     return TF_OK;
 }
 
+// The two passes of the forward direction on their own: a consumer that only needs WHICH pixel lands on each target
+// (the move-reference compositor layer, tf_layer_update_claims) takes the claim plane of the scatter pass and the
+// flow of the gather pass is never formed.
+extern "C" int tf_flow_forward_claims(const float* flow, const tf_flow_op* ops, int n_ops, const float* mask,
+                                      int32_t* claims, int height, int width, void* stream) {
+    TF_REQUIRE(flow && claims, TF_ERR_INVALID_ARG, "tf_flow_forward_claims: null argument");
+    TF_REQUIRE(height > 0 && width > 0, TF_ERR_SHAPE, "tf_flow_forward_claims: bad shape %dx%d", height, width);
+    if (int e = require_sm100()) return e;
+    FlowOps packed;
+    if (int e = pack_flow_ops(ops, n_ops, packed)) return e;
+    cudaStream_t st = as_stream(stream);
+    ScopedKernelTimer timer(TFK_POST_FORWARD, st);
+    k_post_forward_scatter<<<dim3(ceil_div(width, 256), height), 256, 0, st>>>(reinterpret_cast<const float2*>(flow), mask,
+                                                                              claims, height, width, packed);
+    TF_LAUNCHED();
+    return TF_OK;
+}
+
+extern "C" int tf_flow_from_claims(int32_t* claims, float* flow_out, int height, int width, void* stream) {
+    TF_REQUIRE(flow_out && claims, TF_ERR_INVALID_ARG, "tf_flow_from_claims: null argument");
+    TF_REQUIRE(height > 0 && width > 0, TF_ERR_SHAPE, "tf_flow_from_claims: bad shape %dx%d", height, width);
+    if (int e = require_sm100()) return e;
+    cudaStream_t st = as_stream(stream);
+    k_post_forward_gather<<<dim3(ceil_div(width, 256), height), 256, 0, st>>>(reinterpret_cast<float2*>(flow_out), claims,
+                                                                             height, width, 1.0f / (float)width);
+    TF_LAUNCHED();
+    return TF_OK;
+}
+
 extern "C" int tf_flow_postprocess_to(float* flow, const float* mask, int forward, int32_t* owner, float* out,
                                       int height, int width, void* stream) {
     return tf_flow_postprocess_ex(flow, nullptr, 0, mask, forward, owner, out, height, width, stream);

@@ -395,14 +395,26 @@ __global__ void __launch_bounds__(256, 5) k_fb_polyexp(const float* __restrict__
     if (interior) {
         static_assert(N > 7 || (SH + 2) * GP <= 3 * TY * SP, "staged gray tile must fit in the sV scratch");
         float* sG = &sV[0][0];
-        for (int i = tid; i < (SH + 2) * GW; i += 256) {
-            int r = i / GW, q = i - r * GW;
-            uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(gray + (size_t)(y0 - N - 1 + r) * w + (x0 - 8)) + q);
-            float* d = sG + r * GP + 4 * q;
-            d[0] = (float)(v & 255u);
-            d[1] = (float)((v >> 8) & 255u);
-            d[2] = (float)((v >> 16) & 255u);
-            d[3] = (float)(v >> 24);
+        {   // all of a thread's words requested before the first is unpacked (one wait for memory, not one per word)
+            constexpr int NW = ((SH + 2) * GW + 255) / 256;
+            uint32_t v[NW];
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                int i = tid + 256 * k, r = i / GW, q = i - r * GW;
+                if (i < (SH + 2) * GW)
+                    v[k] = __ldg(reinterpret_cast<const uint32_t*>(gray + (size_t)(y0 - N - 1 + r) * w + (x0 - 8)) + q);
+            }
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                int i = tid + 256 * k, r = i / GW, q = i - r * GW;
+                if (i < (SH + 2) * GW) {
+                    float* d = sG + r * GP + 4 * q;
+                    d[0] = (float)(v[k] & 255u);
+                    d[1] = (float)((v[k] >> 8) & 255u);
+                    d[2] = (float)((v[k] >> 16) & 255u);
+                    d[3] = (float)(v[k] >> 24);
+                }
+            }
         }
         __syncthreads();
         float c0i;
@@ -440,19 +452,36 @@ __global__ void __launch_bounds__(256, 5) k_fb_polyexp(const float* __restrict__
     float c0 = interior ? 0.f
                : FUSE3  ? fb_blur3(gray, min(x0, w - 1), min(y0, h - 1), w, h, k0, k1)
                         : __ldg(img + (size_t)min(y0, h - 1) * w + min(x0, w - 1));
-    for (int i = tid; i < (interior ? 0 : SH * SW); i += 256) {
-        int ly = i / SW, lx = i - ly * SW;
-        int gy = clampi(y0 + ly - N, 0, h - 1), gx = clampi(x0 + lx - N, 0, w - 1);
-        float v;
-        if (FUSE3) {
-            v = fb_blur3(gray, gx, gy, w, h, k0, k1);
+    if (FUSE3) {
+        for (int i = tid; i < (interior ? 0 : SH * SW); i += 256) {
+            int ly = i / SW, lx = i - ly * SW;
+            int gy = clampi(y0 + ly - N, 0, h - 1), gx = clampi(x0 + lx - N, 0, w - 1);
+            float v = fb_blur3(gray, gx, gy, w, h, k0, k1);
             // interior of the tile: publish the pyramid image (debug hook / other consumers)
             if (img_out && ly >= N && ly < N + TY && lx >= N && lx < N + TX && y0 + ly - N < h && x0 + lx - N < w)
                 img_out[(size_t)gy * w + gx] = v;
-        } else {
-            v = __ldg(img + (size_t)gy * w + gx);
+            sI[ly * SP + lx] = v - c0;
         }
-        sI[ly * SP + lx] = v - c0;
+    } else {
+        // the footprint in batches of BATCH loads per thread, all requested before the first is used: a thread waits
+        // for memory once per batch instead of once per element (the loop is 7.5 elements long for n = 5)
+        constexpr int BATCH = 4;
+        for (int i0 = tid; i0 < SH * SW; i0 += 256 * BATCH) {
+            float v[BATCH];
+#pragma unroll
+            for (int k = 0; k < BATCH; k++) {
+                int i = i0 + 256 * k;
+                int ly = i / SW, lx = i - ly * SW;
+                int gy = clampi(y0 + ly - N, 0, h - 1), gx = clampi(x0 + lx - N, 0, w - 1);
+                if (i < SH * SW) v[k] = __ldg(img + (size_t)gy * w + gx);
+            }
+#pragma unroll
+            for (int k = 0; k < BATCH; k++) {
+                int i = i0 + 256 * k;
+                int ly = i / SW, lx = i - ly * SW;
+                if (i < SH * SW) sI[ly * SP + lx] = v[k] - c0;
+            }
+        }
     }
     __syncthreads();
     // vertical pass: SW columns x (TY / 4) row groups
@@ -644,14 +673,26 @@ __global__ void __launch_bounds__(256, 5) k_fb_polyexp_folded(const uint8_t* __r
         // 32-bit loads of columns x0 - 8 .. x0 + TX + 7; the tile's first pixel is subtracted (see k_fb_polyexp)
         constexpr int SH = TY + 2 * MF, GW = (TX + 16) / 4, SKIP = 8 - MF;
         const float c0 = (float)__ldg(gray + (size_t)y0 * w + x0);
-        for (int i = tid; i < SH * GW; i += 256) {
-            int r = i / GW, q = i - r * GW;
-            uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(gray + (size_t)(y0 - MF + r) * w + (x0 - 8)) + q);
-            float* d = sI + r * SP + 4 * q - SKIP;
+        {   // all of a thread's words requested before the first is unpacked (one wait for memory, not one per word)
+            constexpr int NW = (SH * GW + 255) / 256;
+            uint32_t v[NW];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                int lx = 4 * q + j - SKIP;
-                if (lx >= 0 && lx < TX + 2 * MF) d[j] = (float)((v >> (8 * j)) & 255u) - c0;
+            for (int k = 0; k < NW; k++) {
+                int i = tid + 256 * k, r = i / GW, q = i - r * GW;
+                if (i < SH * GW)
+                    v[k] = __ldg(reinterpret_cast<const uint32_t*>(gray + (size_t)(y0 - MF + r) * w + (x0 - 8)) + q);
+            }
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                int i = tid + 256 * k, r = i / GW, q = i - r * GW;
+                if (i < SH * GW) {
+                    float* d = sI + r * SP + 4 * q - SKIP;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        int lx = 4 * q + j - SKIP;
+                        if (lx >= 0 && lx < TX + 2 * MF) d[j] = (float)((v[k] >> (8 * j)) & 255u) - c0;
+                    }
+                }
             }
         }
         __syncthreads();
@@ -1161,7 +1202,7 @@ static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int var
             int e = big ? fb_iterate_half<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, 24, st)
                         : fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st);
             if (e) return e;
-        } else if (variant == 25 || (variant >= 27 && variant <= 29)) {
+        } else if (variant == 25 || (variant >= 27 && variant <= 30)) {
             const bool big = (size_t)L.w * L.h >= (size_t)400000;
             int e = big ? fb_iterate_pack<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, variant, st)
                         : fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st);
@@ -1190,7 +1231,7 @@ extern "C" int tf_farneback_solve(tf_farneback* h, int slot_left, int slot_right
     TF_REQUIRE(h && flow, TF_ERR_INVALID_ARG, "tf_farneback_solve: null argument");
     TF_REQUIRE(slot_ok(slot_left) && slot_ok(slot_right) && h->has_frame[slot_left] && h->has_frame[slot_right],
                TF_ERR_INVALID_ARG, "tf_farneback_solve: slots must be prepared slots in [0, %d)", FB_SLOTS);
-    TF_REQUIRE(variant >= 0 && variant <= 29 && variant != 26, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
+    TF_REQUIRE(variant >= 0 && variant <= 30 && variant != 26, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
     TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_solve: flow must be 8-byte aligned");
     cudaStream_t st = as_stream(stream);
     float2* out = reinterpret_cast<float2*>(flow);
@@ -1206,7 +1247,7 @@ extern "C" int tf_farneback_step_lane(tf_farneback* h, int lane, int new_slot, c
                "tf_farneback_step: slots must be in [0, %d)", FB_SLOTS);
     TF_REQUIRE((new_slot == slot_left) != (new_slot == slot_right), TF_ERR_INVALID_ARG,
                "tf_farneback_step: the new frame must be exactly one side of the pair");
-    TF_REQUIRE(variant >= 0 && variant <= 29 && variant != 26, TF_ERR_INVALID_ARG, "tf_farneback_step: unknown variant %d", variant);
+    TF_REQUIRE(variant >= 0 && variant <= 30 && variant != 26, TF_ERR_INVALID_ARG, "tf_farneback_step: unknown variant %d", variant);
     TF_REQUIRE(variant != 1 || lane == 0, TF_ERR_INVALID_ARG,
                "tf_farneback_step: the unfused reference kernels (variant 1) share their scratch, lane 0 only");
     TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_step: flow must be 8-byte aligned");

@@ -115,7 +115,7 @@ __device__ __forceinline__ void phase_b(float* __restrict__ ring, int old_sel, i
 
 // ---- phase C: horizontal window sums + 2x2 solve + store; one thread per (row, 4-column segment), a warp = 4 segments
 // x 8 rows ----
-template <typename G>
+template <typename G, bool HALF_READS = false>
 __device__ __forceinline__ void phase_c(const float* __restrict__ ring, int old_sel, float2* __restrict__ flow_out,
                                         int tid, int x0, int ty, int nout, int w, int h, float reg, int clip) {
     constexpr int NWI = ((G::TY + 7) / 8) * (G::TX / 16);
@@ -147,7 +147,7 @@ __device__ __forceinline__ void phase_c(const float* __restrict__ ring, int old_
         }
         float2 sp[2][4];  // [pair plane][output]: (G11, G12), (G22, h1)
 #pragma unroll
-        for (int p = 0; p < 2; p++) {
+        for (int p = 0; p < (HALF_READS ? 1 : 2); p++) {  // HALF_READS: timing experiment (mode 6), wrong flows
             const float4* rp = reinterpret_cast<const float4*>(ring + p * G::PSTR + old_sel * G::PHALF + row * (2 * G::PP) + seg * 8);
             float2 win[2 * G::NQ2];
 #pragma unroll
@@ -165,6 +165,10 @@ __device__ __forceinline__ void phase_c(const float* __restrict__ ring, int old_
                 acc = __fadd2_rn(acc, __fadd2_rn(win[o + G::WIN - 1], neg2(win[o - 1])));
                 sp[p][o] = acc;
             }
+        }
+        if (HALF_READS) {
+#pragma unroll
+            for (int o = 0; o < 4; o++) sp[1][o] = make_float2(sp[0][o].y, sp[0][o].x);
         }
         float2* dst = flow_out + (size_t)y * w + xg;
         const bool wide = xg + 4 <= w && (w & 1) == 0;
@@ -396,7 +400,8 @@ __device__ __forceinline__ void phase_a_pair(float* __restrict__ ring, int new_s
     }
 }
 
-// MODE 1: rows one at a time; 3: row pairs; 4 / 5: timing experiments (phase A only / phases B + C only)
+// MODE 1: rows one at a time; 3: row pairs; 4 / 5 / 6: timing experiments (phase A only / phases B + C only / B + C with
+// phase C reading 14 instead of 23 128-bit words)
 template <int MR, bool HAS_FLOW, int MODE>
 __global__ void __launch_bounds__(256, 4)
     k_fb_iter_pack(const float4* __restrict__ R0q, const float* __restrict__ R0e, const float4* __restrict__ R1q,
@@ -420,7 +425,7 @@ __global__ void __launch_bounds__(256, 4)
 
     for (int hh = 0; hh <= ntiles; hh++) {
         const int new_sel = hh & 1;
-        if (activeA && MODE != 5) {  // (modes 4 / 5: timing experiments, phase A only / phases B + C only)
+        if (activeA && MODE != 5 && MODE != 6) {  // (modes 4 / 5: timing experiments, phase A only / phases B + C only)
             const int gy_base = y0 - MR + hh * G::TY;
             if constexpr (MODE == 3)
                 phase_a_pair<G, HAS_FLOW>(ring, new_sel, R0q, R0e, R1q, R1e, flow_in, w, h, gy_base, gxA, lxA, rA, sxA, edge);
@@ -434,7 +439,7 @@ __global__ void __launch_bounds__(256, 4)
         __syncthreads();
         if (MODE != 4) phase_b<G>(ring, old_sel, tid);
         __syncthreads();
-        if (MODE != 4) phase_c<G>(ring, old_sel, flow_out, tid, x0, ty, nout, w, h, reg, clip);
+        if (MODE != 4) phase_c<G, MODE == 6>(ring, old_sel, flow_out, tid, x0, ty, nout, w, h, reg, clip);
         __syncthreads();  // the next tile's phase A overwrites the half phase C just read
     }
 }
@@ -512,6 +517,7 @@ static int fb_iterate_pack(tf_farneback* h, FbLevel& L, const RT* R0, const RT* 
         e = variant == 27   ? fb_launch_pack<MR, 3>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)    \
             : variant == 28 ? fb_launch_pack_exp<MR, 4>(R0f, R1f, in, dst, L.w, L.h, scale, c, st) \
             : variant == 29 ? fb_launch_pack_exp<MR, 5>(R0f, R1f, in, dst, L.w, L.h, scale, c, st) \
+            : variant == 30 ? fb_launch_pack_exp<MR, 6>(R0f, R1f, in, dst, L.w, L.h, scale, c, st) \
                             : fb_launch_pack<MR, 1>(R0f, R1f, in, dst, L.w, L.h, scale, c, st);   \
         break;
                 TF_FBP(4) TF_FBP(5) TF_FBP(6) TF_FBP(7) TF_FBP(8) TF_FBP(9) TF_FBP(10) TF_FBP(11) TF_FBP(12)

@@ -366,6 +366,10 @@ class CvFlowSource(FlowSource):
         self.prev_gray = gray
         return flow
 
+    def _reads_prev_flow(self) -> bool:
+        # Horn-Schunck starts from the previous (post-processed, aliased) flow
+        return super()._reads_prev_flow() or self.config.method == CvFlowSource.Method.HORN_SCHUNCK
+
     def next(self) -> torch.Tensor:
         if (self.config.method == CvFlowSource.Method.FARNEBACK and self.pairs_in_flight > 1
                 and self.prev_gray is not None

@@ -205,7 +205,9 @@ class FlowSource:
         self.prev_flow = None
         self.lock_start = None
         self.lock_expr_stay_index = 0
-        #: "numpy" (reference behaviour) or "device" (CUDA tensors, no D2H per frame)
+        #: "numpy" (reference behaviour), "device" (CUDA tensors, no D2H per frame) or "claims": as "device", but a
+        #: FORWARD flow whose only consumer is the compositor is handed out as ``ops.ForwardClaims`` (the scatter pass's
+        #: claim plane; ``Compositor.step`` consumes it, ``.tensor()`` forms the flow for anyone else)
         self.output = "numpy"
         self.start_frame = ckpt_start_frame
         self.rewind()
@@ -285,7 +287,7 @@ class FlowSource:
             self.read_next_flow()
         self.output_frame_index += 1
         out = self.post_process(flow)
-        if self.output == "device":
+        if self.output in ("device", "claims"):
             return out
         return out.cpu().numpy()
 
@@ -296,6 +298,10 @@ class FlowSource:
         arr, n = ops._pack_flow_ops(pending)
         ops.check(ops._lib.load().tf_flow_filters(ops.ptr(flow), arr, n, None, ops.ptr(flow), self.height,
                                                   self.width, ops.stream_ptr()))
+
+    def _reads_prev_flow(self) -> bool:
+        """Is ``prev_flow`` (which aliases the buffer ``post_process`` edits in place, quirk Q5) read again later?"""
+        return self.lock_expr_stay is not None or self.lock_expr_skip is not None
 
     def post_process(self, raw):
         """filters -> mask -> kernel -> [forward: clip, round, scatter] -> clip, on the device.
@@ -329,6 +335,10 @@ class FlowSource:
                 pending.append(flt.op(t))
             else:
                 flt.apply(flow, t)
+        if (self.output == "claims" and self._post.forward and self._post.kernel is None
+                and not self._reads_prev_flow()):
+            # nobody reads ``raw`` again, so the in-place edits of the reference are unobservable: scatter pass only
+            return self._post.claims(flow, ops=pending)
         if not self._post.copies:
             return self._post(flow, ops=pending)
         if pending:

@@ -220,6 +220,52 @@ def _pack_flow_ops(ops):
     return arr, len(ops)
 
 
+class ForwardClaims:
+    """A FORWARD flow in the form the scatter pass of ``post_process`` leaves it (source.py:349-360): an int32 plane in
+    which every moved pixel claimed its target (``numpy.put``: the last source in raster order wins).  The flow the
+    reference returns is "claimant - own position"; the move-reference compositor layer only needs the claimant, so
+    ``Compositor.step`` consumes the plane directly (``tf_layer_update_claims``) and that flow is never written to or
+    read from HBM.  Any other consumer calls ``tensor()``, which forms the flow (once) exactly as ``PostProcess`` would
+    have.  The plane belongs to the ``PostProcess`` that made it and is recycled: use a claims object before asking
+    the source for ``PostProcess.CLAIM_PLANES`` more flows."""
+
+    def __init__(self, post, plane):
+        self._post, self._plane, self._flow, self._state = post, plane, None, "claims"
+        self.shape = (post.h, post.w, 2)
+
+    @property
+    def live(self) -> bool:
+        """True while the claim plane still holds this flow (not consumed, not turned into a tensor, not recycled)."""
+        return self._state == "claims"
+
+    def take(self) -> torch.Tensor:
+        """Hand the claim plane to a consumer that zeroes it (the compositor layer)."""
+        if self._state != "claims":
+            raise RuntimeError(f"this forward flow's claim plane is gone ({self._state})")
+        self._state = "consumed by the compositor"
+        return self._plane
+
+    def tensor(self) -> torch.Tensor:
+        """The flow as the (H, W, 2) float32 device tensor ``PostProcess.__call__`` returns."""
+        if self._state == "tensor":
+            return self._flow
+        if self._state != "claims":
+            raise RuntimeError(f"this forward flow's claim plane is gone ({self._state}): ask for the tensor before "
+                               "the compositor consumes it, or set the source's output to 'device'")
+        out = torch.empty(self.shape, dtype=torch.float32, device="cuda")
+        check(self._post.lib.tf_flow_from_claims(ptr(self._plane), ptr(out), self._post.h, self._post.w, stream_ptr()))
+        self._flow, self._state = out, "tensor"
+        return out
+
+    def _expire(self):
+        if self._state == "claims":
+            self._plane.zero_()
+            self._state = "recycled before use"
+
+    def cpu(self):
+        return self.tensor().cpu()
+
+
 class PostProcess:
     """``FlowSource.post_process`` (flow/sources/source.py:337-363) on a device flow: elementwise filters ->
     mask -> [convolution kernel] -> [forward: clip, round, scatter] -> clip."""
@@ -235,6 +281,29 @@ class PostProcess:
             if self.kernel.ndim != 2:
                 raise ValueError(f"the flow kernel must be 2-D, got shape {tuple(self.kernel.shape)}")
             self._tmp = torch.empty((self.h, self.w, 2), dtype=torch.float32, device="cuda")
+        self._claim_ring, self._claim_next = [], 0
+
+    CLAIM_PLANES = 4
+
+    def claims(self, flow: torch.Tensor, ops=None) -> ForwardClaims:
+        """Forward direction without a convolution kernel: filters + mask + clip + round + the scatter pass only; the
+        result is a ``ForwardClaims`` (``flow`` itself is left untouched)."""
+        if not self.forward or self.kernel is not None:
+            raise ValueError("claims() is the forward direction's scatter pass (no convolution kernel)")
+        flow = _cuda(flow, torch.float32, "flow")
+        if tuple(flow.shape) != (self.h, self.w, 2):
+            raise ValueError(f"flow must be ({self.h}, {self.w}, 2), got {tuple(flow.shape)}")
+        if len(self._claim_ring) < self.CLAIM_PLANES:
+            self._claim_ring.append([torch.zeros((self.h, self.w), dtype=torch.int32, device="cuda"), None])
+        slot = self._claim_ring[self._claim_next % len(self._claim_ring)]
+        self._claim_next += 1
+        if slot[1] is not None:
+            slot[1]._expire()       # an unused claims object from CLAIM_PLANES flows ago: its plane is cleared
+        arr, n = _pack_flow_ops(ops)
+        check(self.lib.tf_flow_forward_claims(ptr(flow), arr, n, ptr(self.mask), ptr(slot[0]), self.h, self.w,
+                                              stream_ptr()))
+        slot[1] = ForwardClaims(self, slot[0])
+        return slot[1]
 
     def __call__(self, flow: torch.Tensor, out: torch.Tensor | None = None, ops=None) -> torch.Tensor:
         """In place by default; ``out`` (same shape, may be peer memory) receives the result instead and ``flow``

@@ -266,6 +266,12 @@ class Pipeline:
                 mask = load_bool_mask(pc.introduction_path, (height, width), True)
                 interfaces.setdefault(li, []).append(PixmapSourceInterface(q, mask))
         self.compositor.set_sources(interfaces)
+        # the compositor is the flow's only consumer: forward flows may travel as the scatter pass's claim plane
+        c = self.config
+        if (not self.extra_flow_sources and c.flows_merging_function == "first" and self._scale == (1, 1)
+                and self.flow_output is None and not c.view_flow and not c.view_flow_magnitude
+                and os.environ.get("TFB200_FORWARD_CLAIMS", "1") != "0"):
+            self.flow_source.output = "claims"
 
     # -- per-frame pieces ----------------------------------------------------------------------------
     def _upscale(self, flow: torch.Tensor) -> torch.Tensor:
