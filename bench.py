@@ -236,6 +236,9 @@ def workload_config(cfg, extra=None):
         d["pairs_in_flight"] = max(1, min(2, int(os.environ.get("TFB200_FB_LANES", "2"))))
     if cfg["method"] == "lukas-kanade":
         d["lk_step"] = cfg["lk_step"]
+    if cfg["direction"] == "forward":
+        d["forward_flow"] = ("the scatter pass's claim plane goes straight to the compositor layer (no gather pass, no flow "
+                             "tensor) when a single move-reference layer is the only consumer")
     if extra:
         d.update(extra)
     return d
@@ -899,6 +902,26 @@ def run_sharded(args, cfg, rank, world, local):
             peer_views[address] = raw_tensor(address, (H, W, 2))
         return peer_views[address]
     chunk_state = {"next": None}
+    # forward flows as claim planes (the scatter pass's int32 plane, 4 bytes per pixel) instead of flows: decided on rank 0
+    # (its compositor must take them) and shared below; rank 0 reads them from the flow slots' first halves
+    claims_mode = {"on": False}
+    claim_planes = [[torch.zeros((H, W), dtype=torch.int32, device="cuda") for _ in range(2)] for _ in range(lanes)]
+    claim_clear = [[None, None] for _ in range(lanes)]
+    claim_turn = [0] * lanes
+    peer_claim_views = {}
+
+    def peer_claims_view(address):
+        from transflow_b200.peer import raw_tensor
+        if address not in peer_claim_views:
+            peer_claim_views[address] = raw_tensor(address, (H, W), dtype=torch.int32)
+        return peer_claim_views[address]
+
+    def as_compositor_input(f):
+        """What rank 0's compositor is stepped with: a flow, or (claims mode) the claim plane behind `f`."""
+        if not claims_mode["on"]:
+            return f
+        plane = f if f.dtype == torch.int32 else f.view(torch.int32).reshape(-1)[:H * W].view(H, W)
+        return ops.ForwardClaims.from_plane(posts[0], plane)
 
     def join_lanes():
         main = torch.cuda.current_stream()
@@ -944,7 +967,34 @@ def run_sharded(args, cfg, rank, world, local):
                 if io["host"]:
                     feeder.release()
                 flow.record_stream(main)
-                if outs is None or handoff == "store":
+                if claims_mode["on"] and outs is None:
+                    # rank 0's own pair: scatter pass only, into a plane of its own (consumed -- and zeroed -- by the
+                    # compositor up to a round later)
+                    plane = torch.zeros((H, W), dtype=torch.int32, device="cuda")
+                    plane.record_stream(main)
+                    posts[lane].claims(flow, plane=plane)
+                    flows.append(plane)
+                elif claims_mode["on"]:
+                    # producer: scatter into one of the lane's two planes, copy-engine transfer of the 4-byte claims into
+                    # the first half of rank 0's flow slot, then the plane is cleared for its next use
+                    k = claim_turn[lane] & 1
+                    claim_turn[lane] += 1
+                    plane = claim_planes[lane][k]
+                    if claim_clear[lane][k] is not None:
+                        torch.cuda.current_stream().wait_event(claim_clear[lane][k])
+                    posts[lane].claims(flow, plane=plane)
+                    done = torch.cuda.Event()
+                    done.record()
+                    cs = copy_streams[lane]
+                    with torch.cuda.stream(cs):
+                        cs.wait_event(done)
+                        peer_claims_view(outs[i]).copy_(plane, non_blocking=True)
+                        plane.zero_()
+                        cleared = torch.cuda.Event()
+                        cleared.record(cs)
+                    claim_clear[lane][k] = cleared
+                    flows.append(outs[i])
+                elif outs is None or handoff == "store":
                     flows.append(posts[lane](flow, None if outs is None else outs[i]))
                 else:
                     posts[lane](flow)
@@ -984,7 +1034,7 @@ def run_sharded(args, cfg, rank, world, local):
         count["n"] += 1
         if io["host"] and copied[k] is not None:
             torch.cuda.current_stream().wait_event(copied[k])   # the D2H out of this buffer is done
-        comp.step(flow, rgb[k])
+        comp.step(as_compositor_input(flow), rgb[k])
         fan = fanout_box["f"]
         if io["host"] and fan is not None:
             target = fanout_box["frames"] % world            # frame i leaves through rank i % N's PCIe link
@@ -1019,6 +1069,13 @@ def run_sharded(args, cfg, rank, world, local):
     def fresh_chunk(n):
         chunk_state["next"] = None
         return estimate_chunk(0, n)
+    want_claims = torch.zeros(1, dtype=torch.int32, device="cuda")
+    if (rank == 0 and forward and handoff == "copy" and os.environ.get("TFB200_TRANSPORT", "p2p") == "p2p"
+            and os.environ.get("TFB200_FORWARD_CLAIMS", "1") != "0"
+            and len(comp.layers) == 1 and comp.layers[0].takes_claims()):
+        want_claims += 1
+    dist.broadcast(want_claims, src=0)
+    claims_mode["on"] = bool(int(want_claims))
     fresh_chunk(K)
     # F = cost of a pair INSIDE a producer's run of consecutive chunks (no new prepare, lanes not drained): time 4 chunks
     # that continue one another, as the stream's chunks do
@@ -1031,8 +1088,10 @@ def run_sharded(args, cfg, rank, world, local):
     plan = torch.zeros(2, dtype=torch.float64, device="cuda")
     if rank == 0:
         fl = fresh_chunk(1)[0]
-        accumulate(fl)
-        a_ms = timed(lambda: accumulate(fl), 4)
+        torch.cuda.current_stream().synchronize()
+        copies = [fl.clone() for _ in range(5)]       # (claims mode: the compositor clears the plane it consumes)
+        accumulate(copies.pop())
+        a_ms = timed(lambda: accumulate(copies.pop()), 4)
         plan[0], plan[1] = f_ms, a_ms
         # calibration frames went through the compositor: start the measured stream from a fresh state
         comp = make_compositor(cfg, mask_png, pixmaps, video_rgb)
@@ -1116,7 +1175,7 @@ def run_sharded(args, cfg, rank, world, local):
             while done < replay_frames:
                 n = min(K, replay_frames - done)
                 for f in estimate_chunk(done, n):
-                    comp.step(f, rgb[0])
+                    comp.step(as_compositor_input(f), rgb[0])
                 done += n
             torch.cuda.synchronize()
             check["single_rank_replay"] = state_sum(solo)
@@ -1168,8 +1227,11 @@ def run_sharded(args, cfg, rank, world, local):
                          f"transport {transport}: "
                          + (("the producer's last post-process kernel stores the flow into rank 0's ring over NVLink "
                              "peer memory" if handoff == "store" else
-                             "a copy-engine transfer moves the post-processed flow into rank 0's ring over NVLink peer "
-                             "memory while the lane solves the next pair") +
+                             ("a copy-engine transfer moves the forward scatter's claim plane (int32, 4 bytes per pixel: the "
+                              "compositor reads the claimant directly, no flow is formed) into rank 0's ring over NVLink "
+                              "peer memory while the lane solves the next pair" if claims_mode["on"] else
+                              "a copy-engine transfer moves the post-processed flow into rank 0's ring over NVLink peer "
+                              "memory while the lane solves the next pair")) +
                             ", counters + cuStreamWaitValue32 order it" if transport == "p2p" else
                             "batched NCCL send/recv, receives posted one round ahead"),
                 frames_per_step=stream.frames_per_round * rounds_per_step, state_check=check,
@@ -1184,7 +1246,7 @@ def run_sharded(args, cfg, rank, world, local):
                            "sharded stream: pinned BGR frames H2D on every rank, RGB frames D2H on rank 0"},
             "gpu_launches": int(launches), "clocks": clocks, "frames_timed": frames,
             "pipeline_hbm_frac": frame_bytes * fps / 1e9 / (peak * world),
-            "exchange_bytes_per_step": int(sum(counts[1:]) * K * rounds_per_step * n_px * 8),
+            "exchange_bytes_per_step": int(sum(counts[1:]) * K * rounds_per_step * n_px * (4 if claims_mode["on"] else 8)),
             "scaling_ceiling": {"producers": world - 1, "flow_ms_per_pair": f_ms, "accumulate_ms_per_frame": a_ms,
                                 "fps_if_producers_never_wait": (world - 1) * 1000.0 / f_ms
                                 + ((p0 or 0) / (Q * K)) * 1000.0 / f_ms,

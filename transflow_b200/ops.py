@@ -233,6 +233,14 @@ class ForwardClaims:
         self._post, self._plane, self._flow, self._state = post, plane, None, "claims"
         self.shape = (post.h, post.w, 2)
 
+    @classmethod
+    def from_plane(cls, post, plane: torch.Tensor):
+        """A claims object over a claim plane that did not come from ``post``'s own ring: int32 (H, W) device memory
+        filled by ``tf_flow_forward_claims`` somewhere else (another GPU's scatter pass, copied into a ring slot)."""
+        if plane.dtype != torch.int32 or tuple(plane.shape) != (post.h, post.w) or not plane.is_contiguous():
+            raise ValueError(f"a claim plane is a contiguous int32 ({post.h}, {post.w}) tensor")
+        return cls(post, plane)
+
     @property
     def live(self) -> bool:
         """True while the claim plane still holds this flow (not consumed, not turned into a tensor, not recycled)."""
@@ -285,14 +293,21 @@ class PostProcess:
 
     CLAIM_PLANES = 4
 
-    def claims(self, flow: torch.Tensor, ops=None) -> ForwardClaims:
+    def claims(self, flow: torch.Tensor, ops=None, plane: torch.Tensor | None = None) -> ForwardClaims:
         """Forward direction without a convolution kernel: filters + mask + clip + round + the scatter pass only; the
-        result is a ``ForwardClaims`` (``flow`` itself is left untouched)."""
+        result is a ``ForwardClaims`` (``flow`` itself is left untouched).  ``plane``: the caller's own all-zero int32
+        (H, W) plane instead of one of this object's recycled ones."""
         if not self.forward or self.kernel is not None:
             raise ValueError("claims() is the forward direction's scatter pass (no convolution kernel)")
         flow = _cuda(flow, torch.float32, "flow")
         if tuple(flow.shape) != (self.h, self.w, 2):
             raise ValueError(f"flow must be ({self.h}, {self.w}, 2), got {tuple(flow.shape)}")
+        if plane is not None:
+            made = ForwardClaims.from_plane(self, plane)
+            arr, n = _pack_flow_ops(ops)
+            check(self.lib.tf_flow_forward_claims(ptr(flow), arr, n, ptr(self.mask), ptr(plane), self.h, self.w,
+                                                  stream_ptr()))
+            return made
         if len(self._claim_ring) < self.CLAIM_PLANES:
             self._claim_ring.append([torch.zeros((self.h, self.w), dtype=torch.int32, device="cuda"), None])
         slot = self._claim_ring[self._claim_next % len(self._claim_ring)]
