@@ -255,6 +255,12 @@ def algorithmic_bytes_per_frame(cfg, fb=None) -> float:
     else:
         flow = 2.0 * 1.3125 * n + 16.0 * 3.0 * n / (cfg["lk_step"] ** 2) + 4.0 * n
     post = 24.0 * n if forward else 16.0 * n                 # backward: clip pass reads + writes the flow
+    layers = cfg["layers"]
+    if (forward and len(layers) == 1 and layers[0]["classname"] == "moveref"
+            and os.environ.get("TFB200_FORWARD_CLAIMS", "1") != "0"):
+        # claim-plane path: scatter pass only (flow read 8 + claim write 4); the layer then reads the claim
+        # (4) and clears it (4) where the flow-fed layer reads the flow (8): its 22 / 46 bytes below stay as they are
+        post = 12.0 * n
     comp = 0.0
     for layer in cfg["layers"]:
         kind = layer["classname"]
