@@ -181,6 +181,30 @@ def post_process(flow: np.ndarray, forward: bool, mask=None, kernel=None, filter
     return flow
 
 
+def forward_claims(flow: np.ndarray, mask=None, filters=(), t: float = 0.0) -> np.ndarray:
+    """The claim plane behind the forward direction of ``post_process`` (``source.py:349-360``, the ``numpy.put`` of the
+    source coordinates): int32 (H, W), ``claims[q] = p + 1`` for the LAST pixel p in raster order whose clipped, rounded
+    vector points at q (p != q), 0 where nobody does.  ``post_process(flow, True)`` is exactly ``claimant - position``
+    (0 where unclaimed), which is what the device's ``tf_flow_forward_claims`` / ``tf_layer_update_claims`` pair relies on
+    (DESIGN.md 4a).  ``flow`` is not modified."""
+    flow = np.array(flow, dtype=np.float32, copy=True)
+    for name, value in filters:
+        apply_filter(flow, name, value, t)
+    h, w = flow.shape[:2]
+    if mask is not None:
+        flow = np.multiply(np.asarray(mask, np.float32).reshape(h, w, 1), flow)
+    xs = np.arange(w, dtype=np.int32)[None, :]
+    ys = np.arange(h, dtype=np.int32)[:, None]
+    np.clip(flow[..., 0], -xs, w - 1 - xs, out=flow[..., 0])
+    np.clip(flow[..., 1], -ys, h - 1 - ys, out=flow[..., 1])
+    fi = np.rint(flow).astype(np.int32)
+    off = (fi[..., 1] * w + fi[..., 0]).ravel()
+    src = np.nonzero(off)[0]
+    claims = np.zeros(h * w, dtype=np.int32)
+    claims[src + off[src]] = src + 1         # duplicate targets: last (largest) source wins
+    return claims.reshape(h, w)
+
+
 def merge_flows(flows, mode: str) -> np.ndarray:
     """``Pipeline.FLOW_MERGING_FUNCTIONS[mode](flows)`` (``pipeline.py:149-158``, helpers ``utils.py:359-381``).
     Like the reference, ``maskbin`` overwrites the extra flows in place."""

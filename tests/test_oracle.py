@@ -265,3 +265,27 @@ def test_philox_restatement_matches_random123_known_answers():
     assert abs(u.mean() - 0.5) < 0.03
     # a pixel pair shares one block; frames and seeds give unrelated fields
     assert not np.array_equal(u, reset_draws(0x5EED, 4, 33, 47)) and not np.array_equal(u, reset_draws(1, 3, 33, 47))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_forward_claims_are_the_forward_flow(seed):
+    """DESIGN.md 4a on the CPU: the claim plane of the forward scatter determines the forward flow (claimant - position,
+    0 where unclaimed), and a move-reference layer fed with that flow fetches exactly the claimant's record -- so a layer
+    that reads the claims needs no flow.  ``post_process`` is pinned to the reference by the golden flows above."""
+    from oracle import flow_cv as F
+    rng = np.random.default_rng(seed)
+    h, w = 37, 53
+    raw = rng.uniform(-7, 7, (h, w, 2)).astype(np.float32)
+    raw[rng.random((h, w)) < 0.25] = 0
+    mask = rng.random((h, w)).astype(np.float32) if seed == 1 else None
+    filters = [("scale", 1.5)] if seed == 2 else []
+    claims = F.forward_claims(raw, mask=mask, filters=filters)
+    want = F.post_process(raw.copy(), True, mask=mask, filters=filters)
+    ys, xs = np.mgrid[0:h, 0:w]
+    claimant = np.where(claims > 0, claims - 1, ys * w + xs)
+    got = np.stack([claimant % w - xs, claimant // w - ys], axis=-1).astype(np.float32)
+    np.testing.assert_array_equal(got, np.asarray(want, np.float32))
+    # what the compositor's move step fetches for that flow (movement.py:25-33: p + rint(fy) * w + rint(fx)) is the claimant
+    off = np.rint(want[..., 1]).astype(np.int64) * w + np.rint(want[..., 0]).astype(np.int64)
+    np.testing.assert_array_equal((ys * w + xs + off), claimant)
+    assert ((claims > 0) & (claimant != ys * w + xs)).mean() > 0.3        # most pixels are claimed by another pixel
