@@ -1276,6 +1276,12 @@ def main():
     ap.add_argument("--lk-step", type=int, default=1, help="lk_step of the Lucas-Kanade config (1 = dense)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries ONE JSON line: whatever a library writes to file descriptor 1 meanwhile (NCCL's version banner at
+    # communicator creation, for one) goes to stderr instead, and the line is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
