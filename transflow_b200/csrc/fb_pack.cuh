@@ -1,4 +1,4 @@
-// Fused Farneback iteration, "packed half-buffer" kernel (solve variants 25 and 27-29, checked experiments -- not the
+// Fused Farneback iteration, "packed half-buffer" kernel (solve variants 25 and 27-30, checked experiments -- not the
 // default; what they showed is in DESIGN.md 5c): the arithmetic and the tile walk of
 // fb_half.cuh's default configuration (64-column strips, 256 threads, 4 CTAs / SM, halves of 2m matrix rows, 4-column
 // phase C) with the instruction count cut where the default spends issue slots on work that is not FP math
@@ -483,15 +483,16 @@ static int fb_launch_pack(const float* R0, const float* R1, const float2* in, fl
     return TF_OK;
 }
 
-// timing experiments (phase A only / phases B + C only: wrong flows by construction), window radius 7 only
+// timing experiments (phase A only / phases B + C only / B + C with fewer phase-C reads: wrong flows by construction),
+// window radius 7 only
 template <int MR, int MODE>
 static int fb_launch_pack_exp(const float* R0, const float* R1, const float2* in, float2* dst, int w, int h, double scale,
                               int clip, cudaStream_t st) {
     if constexpr (MR == 7) return fb_launch_pack<7, MODE>(R0, R1, in, dst, w, h, scale, clip, st);
-    else return fail(TF_ERR_INVALID_ARG, "variants 28 / 29 are timing experiments for winsize 15");
+    else return fail(TF_ERR_INVALID_ARG, "variants 28 - 30 are timing experiments for winsize 15");
 }
 
-// variants 25 (rows one at a time) / 27 (row pairs) / 28, 29 (timing experiments); window radii below 4 and half-precision R storage stay on
+// variants 25 (rows one at a time) / 27 (row pairs) / 28 - 30 (timing experiments); window radii below 4 and half-precision R storage stay on
 // the rolling-tile kernel, like fb_iterate_half
 template <typename RT>
 static int fb_iterate_pack(tf_farneback* h, FbLevel& L, const RT* R0, const RT* R1, float2* final_buf,
