@@ -91,7 +91,8 @@ TF_API int tf_farneback_prepare(tf_farneback* h, int slot, const uint8_t* gray, 
  * (M and double vertical sums materialised in HBM); 0 / 2 = fused column-streaming kernel with
  * float / double sums in shared memory (kept for comparison); 17-24 = configurations of the half-buffer kernel and
  * the TMA-fed ring kernels (fb_ring.cuh); 25 = packed half-buffer kernel (channel pairs in shared memory, FADD2 window
- * sums, fb_pack.cuh), 27 = the same with pairs of rows sharing their middle tap row -- both bit-identical to 8;
+ * sums, fb_pack.cuh), 27 / 31 = the same with pairs of rows sharing their middle tap row (31: one wait per pair, 80
+ * registers, 3 CTAs per SM) -- all bit-identical to 8 and not faster;
  * 28 / 29 / 30 = timing experiments (phase A only / phases B + C only / B + C with 14 instead of 23 phase-C reads of
  * variant 25: NOT a flow), winsize 15 only.
  * If clip != 0 the final clip of FlowSource.post_process (source.py:361-362) is fused into

@@ -298,9 +298,9 @@ def test_farneback_edge_sizes(shape, variant):
     assert mean <= 1e-3 and mx <= 2e-2, (mean, mx)
 
 
-@pytest.mark.parametrize("variant", [9, 10, 11, 12, 13, 14, 15, 16, 18, 19, 20, 21, 22, 23, 24, 25, 27])
+@pytest.mark.parametrize("variant", [9, 10, 11, 12, 13, 14, 15, 16, 18, 19, 20, 21, 22, 23, 24, 25, 27, 31])
 def test_farneback_staged_kernel_is_bit_identical_to_default(variant):
-    """Variants 25 / 27: the packed half-buffer kernel (channel pairs in shared memory, FADD2 window sums; 27 shares the
+    """Variants 25 / 27: the packed half-buffer kernel (channel pairs in shared memory, FADD2 window sums; 27 / 31 share the
     middle tap row of a pair of rows).  Variants 9 / 10 (R1 box staged in shared memory by bulk copies + mbarrier, global fallback outside the box; 64-
     or 32-column strips) run the same arithmetic as the default kernel: identical flows, also when the motion
     exceeds the staging margin."""

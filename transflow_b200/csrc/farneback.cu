@@ -1202,7 +1202,7 @@ static int solve_impl(tf_farneback* h, int sl, int sr, float2* flow_out, int var
             int e = big ? fb_iterate_half<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, 24, st)
                         : fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st);
             if (e) return e;
-        } else if (variant == 25 || (variant >= 27 && variant <= 30)) {
+        } else if (variant == 25 || (variant >= 27 && variant <= 31)) {
             const bool big = (size_t)L.w * L.h >= (size_t)400000;
             int e = big ? fb_iterate_pack<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, variant, st)
                         : fb_iterate_tile<RT>(h, L, R0, R1, final_buf, other_buf, zero_init, clip && finest, finest, st);
@@ -1231,7 +1231,7 @@ extern "C" int tf_farneback_solve(tf_farneback* h, int slot_left, int slot_right
     TF_REQUIRE(h && flow, TF_ERR_INVALID_ARG, "tf_farneback_solve: null argument");
     TF_REQUIRE(slot_ok(slot_left) && slot_ok(slot_right) && h->has_frame[slot_left] && h->has_frame[slot_right],
                TF_ERR_INVALID_ARG, "tf_farneback_solve: slots must be prepared slots in [0, %d)", FB_SLOTS);
-    TF_REQUIRE(variant >= 0 && variant <= 30 && variant != 26, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
+    TF_REQUIRE(variant >= 0 && variant <= 31 && variant != 26, TF_ERR_INVALID_ARG, "tf_farneback_solve: unknown variant %d", variant);
     TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_solve: flow must be 8-byte aligned");
     cudaStream_t st = as_stream(stream);
     float2* out = reinterpret_cast<float2*>(flow);
@@ -1247,7 +1247,7 @@ extern "C" int tf_farneback_step_lane(tf_farneback* h, int lane, int new_slot, c
                "tf_farneback_step: slots must be in [0, %d)", FB_SLOTS);
     TF_REQUIRE((new_slot == slot_left) != (new_slot == slot_right), TF_ERR_INVALID_ARG,
                "tf_farneback_step: the new frame must be exactly one side of the pair");
-    TF_REQUIRE(variant >= 0 && variant <= 30 && variant != 26, TF_ERR_INVALID_ARG, "tf_farneback_step: unknown variant %d", variant);
+    TF_REQUIRE(variant >= 0 && variant <= 31 && variant != 26, TF_ERR_INVALID_ARG, "tf_farneback_step: unknown variant %d", variant);
     TF_REQUIRE(variant != 1 || lane == 0, TF_ERR_INVALID_ARG,
                "tf_farneback_step: the unfused reference kernels (variant 1) share their scratch, lane 0 only");
     TF_REQUIRE(((uintptr_t)flow & 7) == 0, TF_ERR_INVALID_ARG, "tf_farneback_step: flow must be 8-byte aligned");

@@ -1,4 +1,4 @@
-// Fused Farneback iteration, "packed half-buffer" kernel (solve variants 25 and 27-30, checked experiments -- not the
+// Fused Farneback iteration, "packed half-buffer" kernel (solve variants 25 and 27-31, checked experiments -- not the
 // default; what they showed is in DESIGN.md 5c): the arithmetic and the tile walk of
 // fb_half.cuh's default configuration (64-column strips, 256 threads, 4 CTAs / SM, halves of 2m matrix rows, 4-column
 // phase C) with the instruction count cut where the default spends issue slots on work that is not FP math
@@ -400,10 +400,73 @@ __device__ __forceinline__ void phase_a_pair(float* __restrict__ ring, int new_s
     }
 }
 
+// ---- phase A, row pairs with ONE wait per pair (MODE 7): as phase_a_pair, but the three tap rows of a pair and both
+// R0 pixels are requested together, so the longest thread of a tile waits for memory 3 times (7 pairs over 3 row groups)
+// instead of 5 (rows one at a time) or 6 (phase_a_pair).  Only the next pair's FLOWS are prefetched (the addresses depend
+// on them); a lane whose second pixel samples elsewhere fetches its own two rows after the first pixel (extra wait). ----
+template <typename G, bool HAS_FLOW>
+__device__ __forceinline__ void phase_a_pair1(float* __restrict__ ring, int new_sel, const float4* __restrict__ R0q,
+                                              const float* __restrict__ R0e, const float4* __restrict__ R1q,
+                                              const float* __restrict__ R1e, const float2* __restrict__ flow_in, int w,
+                                              int h, int gy_base, int gxA, int lxA, int rA, float sxA, bool edge) {
+    const unsigned uw = (unsigned)w;
+    const float fgx = (float)gxA;
+    int r = 2 * rA;
+    int gy0 = tf::clampi(gy_base + r, 0, h - 1), gy1 = tf::clampi(gy_base + r + 1, 0, h - 1);
+    float2 f0 = make_float2(0.f, 0.f), f1 = f0;
+    if (HAS_FLOW) {
+        f0 = ld_stream(flow_in + ((unsigned)gy0 * uw + (unsigned)gxA));
+        f1 = ld_stream(flow_in + ((unsigned)gy1 * uw + (unsigned)gxA));
+    }
+    float2* d01 = reinterpret_cast<float2*>(ring + new_sel * G::PHALF) + r * G::PP + lxA;
+    float* d4 = ring + 2 * G::PSTR + new_sel * G::SHALF + r * G::PS + lxA;
+#pragma unroll 1
+    for (; r < G::TY; r += 2 * G::NG) {
+        const float fx0 = fgx + f0.x, fy0 = (float)gy0 + f0.y;
+        const float fx1 = fgx + f1.x, fy1 = (float)gy1 + f1.y;
+        const int xa = __float2int_rd(fx0), ya = __float2int_rd(fy0);
+        const int xb = __float2int_rd(fx1), yb = __float2int_rd(fy1);
+        const bool in0 = (unsigned)xa < (unsigned)(w - 1) && (unsigned)ya < (unsigned)(h - 1);
+        const bool in1 = (unsigned)xb < (unsigned)(w - 1) && (unsigned)yb < (unsigned)(h - 1);
+        const bool share = in0 && xb == xa && yb == ya + 1;
+        Taps U, V, W;
+        if (in0) {
+            const unsigned q = (unsigned)ya * uw + (unsigned)xa;
+            U = load_taps(R1q, R1e, q);
+            V = load_taps(R1q, R1e, q + uw);
+        }
+        const unsigned qb = (unsigned)yb * uw + (unsigned)xb;
+        if (in1 && share) W = load_taps(R1q, R1e, qb + uw);
+        const unsigned ata = (unsigned)gy0 * uw + (unsigned)gxA, atb = (unsigned)gy1 * uw + (unsigned)gxA;
+        const float4 a0 = ld_stream(R0q + ata), a1 = ld_stream(R0q + atb);
+        const float a04 = ld_stream(R0e + ata), a14 = ld_stream(R0e + atb);
+        matrix_pixel<G>(a0, a04, f0, fx0, fy0, in0, gy0, h, sxA, edge, U, V, d01, d4);
+        if (in1 && !share) {
+            V = load_taps(R1q, R1e, qb);
+            W = load_taps(R1q, R1e, qb + uw);
+        }
+        const float2 g1 = f1;
+        const int gyb = gy1;
+        // the next pair's flows (its addresses need them first), requested once the first pixel's taps are dead: the second
+        // pixel's arithmetic and the other warps of the scheduler cover their latency
+        if (r + 2 * G::NG < G::TY) {
+            gy0 = tf::clampi(gy_base + r + 2 * G::NG, 0, h - 1);
+            gy1 = tf::clampi(gy_base + r + 2 * G::NG + 1, 0, h - 1);
+            if (HAS_FLOW) {
+                f0 = ld_stream(flow_in + ((unsigned)gy0 * uw + (unsigned)gxA));
+                f1 = ld_stream(flow_in + ((unsigned)gy1 * uw + (unsigned)gxA));
+            }
+        }
+        matrix_pixel<G>(a1, a14, g1, fx1, fy1, in1, gyb, h, sxA, edge, V, W, d01 + G::PP, d4 + G::PS);
+        d01 += 2 * G::NG * G::PP;
+        d4 += 2 * G::NG * G::PS;
+    }
+}
+
 // MODE 1: rows one at a time; 3: row pairs; 4 / 5 / 6: timing experiments (phase A only / phases B + C only / B + C with
 // phase C reading 14 instead of 23 128-bit words)
 template <int MR, bool HAS_FLOW, int MODE>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, (MODE == 7 ? 3 : 4))   // mode 7 holds three tap rows: 80 registers, 3 CTAs / SM
     k_fb_iter_pack(const float4* __restrict__ R0q, const float* __restrict__ R0e, const float4* __restrict__ R1q,
                    const float* __restrict__ R1e, const float2* __restrict__ flow_in, float2* __restrict__ flow_out,
                    int w, int h, float reg, int rows_per_cta, int clip) {
@@ -417,7 +480,7 @@ __global__ void __launch_bounds__(256, 4)
     const int ntiles = (y1 - y0 + G::TY - 1) / G::TY;  // halves 0 .. ntiles (half 0 = prologue)
 
     const int lxA = tid % G::COLS, rA = tid / G::COLS;
-    const bool activeA = rA < G::NG && (MODE != 3 || 2 * rA < G::TY);
+    const bool activeA = rA < G::NG && ((MODE != 3 && MODE != 7) || 2 * rA < G::TY);
     const int gxA = tf::clampi(x0 - MR + lxA, 0, w - 1);
     // does any matrix pixel of this CTA lie in the 5-pixel attenuation border?  (CTA-uniform)
     const bool edge = x0 - MR < 5 || x0 + G::TX + MR > w - 5 || y0 - MR < 5 || y1 + MR > h - 5;
@@ -427,7 +490,9 @@ __global__ void __launch_bounds__(256, 4)
         const int new_sel = hh & 1;
         if (activeA && MODE != 5 && MODE != 6) {  // (modes 4 / 5: timing experiments, phase A only / phases B + C only)
             const int gy_base = y0 - MR + hh * G::TY;
-            if constexpr (MODE == 3)
+            if constexpr (MODE == 7)
+                phase_a_pair1<G, HAS_FLOW>(ring, new_sel, R0q, R0e, R1q, R1e, flow_in, w, h, gy_base, gxA, lxA, rA, sxA, edge);
+            else if constexpr (MODE == 3)
                 phase_a_pair<G, HAS_FLOW>(ring, new_sel, R0q, R0e, R1q, R1e, flow_in, w, h, gy_base, gxA, lxA, rA, sxA, edge);
             else
                 phase_a<G, HAS_FLOW>(ring, new_sel, R0q, R0e, R1q, R1e, flow_in, w, h, gy_base, gxA, lxA, rA, sxA, edge);
@@ -519,6 +584,7 @@ static int fb_iterate_pack(tf_farneback* h, FbLevel& L, const RT* R0, const RT* 
             : variant == 28 ? fb_launch_pack_exp<MR, 4>(R0f, R1f, in, dst, L.w, L.h, scale, c, st) \
             : variant == 29 ? fb_launch_pack_exp<MR, 5>(R0f, R1f, in, dst, L.w, L.h, scale, c, st) \
             : variant == 30 ? fb_launch_pack_exp<MR, 6>(R0f, R1f, in, dst, L.w, L.h, scale, c, st) \
+            : variant == 31 ? fb_launch_pack<MR, 7>(R0f, R1f, in, dst, L.w, L.h, scale, c, st)     \
                             : fb_launch_pack<MR, 1>(R0f, R1f, in, dst, L.w, L.h, scale, c, st);   \
         break;
                 TF_FBP(4) TF_FBP(5) TF_FBP(6) TF_FBP(7) TF_FBP(8) TF_FBP(9) TF_FBP(10) TF_FBP(11) TF_FBP(12)
