@@ -14,6 +14,7 @@ import torch
 from .. import _lib
 from .._lib import check, ptr, stream_ptr
 from ..config import LayerConfig
+from ..ops import ForwardClaims
 from ..utils import parse_color
 from .layers import Layer
 from .pixmap_source_interface import PixmapSourceInterface
@@ -41,7 +42,7 @@ class Compositor:
         return (int(r) << 16) | (int(g) << 8) | int(b)
 
     def update(self, flow):
-        if hasattr(flow, "take") and hasattr(flow, "tensor"):
+        if isinstance(flow, ForwardClaims):
             flow = flow.tensor()
         for layer in self.layers:
             layer.update(flow)
@@ -68,8 +69,8 @@ class Compositor:
         if not self.layers:
             out[:, :] = torch.tensor(self.background_color, dtype=torch.uint8, device="cuda")
             return out
-        if hasattr(flow, "take") and hasattr(flow, "tensor"):
-            # ops.ForwardClaims: a single move-reference layer reads the claim plane itself (no flow in HBM at all)
+        if isinstance(flow, ForwardClaims):
+            # a single move-reference layer reads the claim plane itself (no flow in HBM at all)
             if len(self.layers) == 1 and flow.live and self.layers[0].takes_claims():
                 self.layers[0]._update_claims(flow, out, background=self._bg_word)
                 return out

@@ -18,6 +18,7 @@ import torch
 from ... import _lib
 from ..._lib import LAYER_KINDS, RESET_MODES, LayerConfigStruct, PixmapStruct, check, ptr, stream_ptr
 from ...config import LayerConfig
+from ...ops import ForwardClaims
 from ...utils import load_bool_mask, load_float_mask
 
 
@@ -180,7 +181,7 @@ class Layer:
         self._keepalive = (plane, pixmaps, None)
 
     def _update(self, flow, rgb_inout=None, first_layer=False, background=0):
-        if hasattr(flow, "take") and hasattr(flow, "tensor"):       # ops.ForwardClaims outside Compositor.step
+        if isinstance(flow, ForwardClaims):       # outside Compositor.step's claim path: the flow itself
             flow = flow.tensor()
         fl = None if self.KIND == "static" else flow_to_device(flow)
         if fl is not None and tuple(fl.shape) != (self.height, self.width, 2):
